@@ -1,0 +1,131 @@
+/*
+ * ray_b200.h — extensions next to the Futhark-compatible ABI of ray.h.
+ *
+ * The reference has no samples-per-pixel, no custom scenes, no float framebuffer and no multi-GPU
+ * (ray.fut:150-154, 171-174, 246-247); BASELINE.json's configs need all four.  Because
+ * futhark/main.c must stay unmodified, every extension is reachable two ways:
+ *   - environment variables read by futhark_context_new (RAY_SPP, RAY_KERNEL, RAY_RANK, RAY_WORLD,
+ *     RAY_DEVICE), so the unmodified driver can use them, and
+ *   - the explicit C entry points below (plain pointers and sizes; device pointers are raw
+ *     CUDA device addresses, e.g. torch.Tensor.data_ptr()).
+ *
+ * spp semantics: sample s of pixel (row j, column i) uses
+ *   u = (f32(i) + ox_s) / f32(W),  v = (f32(H - j) + oy_s) / f32(H),
+ *   ox_s = frac(f32(s) * 0.7548776662f), oy_s = frac(f32(s) * 0.5698402909f)   [ox_0 = oy_0 = 0]
+ * colours are summed in sample order in f32, multiplied by 1/spp, then quantised as ray.fut:158-162.
+ * At spp = 1 this is bit-identical to the reference's render.
+ */
+#ifndef RAY_B200_EXT_H
+#define RAY_B200_EXT_H
+
+#include "ray.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Render kernels (tuning param "kernel" / env RAY_KERNEL). */
+enum ray_b200_kernel {
+  RAY_B200_KERNEL_AUTO = 0,       /* pick the fastest measured variant */
+  RAY_B200_KERNEL_MEGA = 1,       /* one thread per pixel, whole ray_colour loop (parity anchor) */
+  RAY_B200_KERNEL_PERSISTENT = 2, /* persistent CTAs, TMA-staged BVH, per-lane dynamic path refill */
+  RAY_B200_KERNEL_WAVEFRONT = 3   /* generate -> per-bounce persistent kernel + ray queues -> pack */
+};
+
+/* ---- context extensions ---------------------------------------------------------------------- */
+/* Launch all work of this context on `cuda_stream` (a cudaStream_t / CUstream, e.g.
+ * torch.cuda.current_stream().cuda_stream).  NULL restores the context's own stream. */
+int ray_b200_context_set_stream(struct futhark_context *ctx, void *cuda_stream);
+/* Samples per pixel used by futhark_entry_render (default 1 = the reference). */
+int ray_b200_context_set_spp(struct futhark_context *ctx, int32_t spp);
+int ray_b200_context_set_kernel(struct futhark_context *ctx, int32_t kernel);
+/* This process renders tiles t with t % world == rank (8x4-pixel tiles, row-major tile order). */
+int ray_b200_context_set_shard(struct futhark_context *ctx, int32_t rank, int32_t world);
+int ray_b200_context_device(struct futhark_context *ctx);
+/* Device time in ms of the last render (CUDA events on the context's stream; syncs). */
+int ray_b200_context_last_render_ms(struct futhark_context *ctx, float *ms);
+/* Number of kernel launches issued by this context since creation. */
+int64_t ray_b200_context_launch_count(struct futhark_context *ctx);
+
+/* ---- scenes ------------------------------------------------------------------------------------ */
+/* spheres: n x 7 floats (pos.xyz, colour.xyz, radius) — the `sphere` record of ray.fut:22-24;
+ * cam7: look_from.xyz, look_at.xyz, fov — the rest of `scene`, ray.fut:171-174.  n >= 2 (bvh.fut:65). */
+int ray_b200_scene_from_arrays(struct futhark_context *ctx, struct futhark_opaque_scene **out0,
+                               const float *spheres, int64_t n, const float *cam7);
+/* splitmix64(seed) stream, 7 draws per sphere, camera (0,0,1100)->(0,0,0). */
+int ray_b200_scene_random(struct futhark_context *ctx, struct futhark_opaque_scene **out0, int64_t n,
+                          uint64_t seed);
+int64_t ray_b200_scene_num_spheres(struct futhark_context *ctx, const struct futhark_opaque_scene *s);
+int ray_b200_scene_get_arrays(struct futhark_context *ctx, const struct futhark_opaque_scene *s, float *spheres,
+                              float *cam7);
+
+/* ---- prepared scene introspection (tests compare these with the oracle's LBVH) ----------------- */
+struct ray_b200_bvh_info {
+  int64_t n_leaves, n_inner;
+  int32_t max_depth, refit_sweeps, stale_nodes, smem_nodes;
+  float root_box[6];
+  float camera[12]; /* origin, llc, horizontal, vertical (ray.fut:88-91) */
+};
+int ray_b200_prepared_info(struct futhark_context *ctx, const struct futhark_opaque_prepared_scene *p,
+                           struct ray_b200_bvh_info *info);
+/* Karras-order dump: morton[n], perm[n], left/right/parent[n-1] (leaf i = ~i), boxes[(n-1)*6]. NULLs skipped. */
+int ray_b200_prepared_dump(struct futhark_context *ctx, const struct futhark_opaque_prepared_scene *p,
+                           uint32_t *morton, int32_t *perm, int32_t *left, int32_t *right, int32_t *parent,
+                           float *boxes);
+
+/* Bytes of the packed scene resident in HBM (nodes + sphere geometry + colours). */
+int64_t ray_b200_prepared_device_bytes(struct futhark_context *ctx, const struct futhark_opaque_prepared_scene *p);
+/* Copies the packed scene host -> device again from page-locked memory, asynchronously on the
+ * context's stream (the H2D leg of an end-to-end step; prepare_scene already does it once). */
+int ray_b200_prepared_reupload(struct futhark_context *ctx, struct futhark_opaque_prepared_scene *p);
+
+/* ---- render extensions -------------------------------------------------------------------------- */
+/* render with explicit spp; optional float framebuffer.  out_pix_dev: device int32[h][w] (or NULL);
+ * out_rgb_dev: device float[h][w][3] (or NULL).  Asynchronous on the context's stream.
+ * With a shard set (world > 1) only this rank's pixels are written. */
+int ray_b200_render_into(struct futhark_context *ctx, int32_t *out_pix_dev, float *out_rgb_dev, int64_t h,
+                         int64_t w, int32_t spp, const struct futhark_opaque_prepared_scene *p);
+/* Same, host buffers: H2D of nothing (the scene is resident), D2H of the frame, synchronous.
+ * This is the call bench.py's e2e leg times. */
+int ray_b200_render_host(struct futhark_context *ctx, int32_t *out_pix_host, float *out_rgb_host, int64_t h,
+                         int64_t w, int32_t spp, const struct futhark_opaque_prepared_scene *p);
+/* Like futhark_entry_render but with explicit spp (library-owned result). */
+int ray_b200_entry_render_spp(struct futhark_context *ctx, struct futhark_i32_2d **out0, int64_t h, int64_t w,
+                              int32_t spp, const struct futhark_opaque_prepared_scene *p);
+
+/* ---- multi-GPU tile sharding (one process per GPU; the gather itself is NCCL, done by the host) -- */
+/* Number of 8x4 tiles rank `rank` of `world` owns for an h x w image, and the padded per-rank count
+ * (equal on all ranks, so a plain all_gather / gather works). */
+int64_t ray_b200_shard_tiles(int64_t h, int64_t w, int32_t rank, int32_t world);
+int64_t ray_b200_shard_tiles_padded(int64_t h, int64_t w, int32_t world);
+/* Renders this rank's tiles into a compact tile-major device buffer int32[tiles_padded][32]. */
+int ray_b200_render_shard_into(struct futhark_context *ctx, int32_t *out_tiles_dev, int64_t h, int64_t w,
+                               int32_t spp, const struct futhark_opaque_prepared_scene *p);
+/* gathered_dev: int32[world][tiles_padded][32] (rank-major, as produced by an NCCL gather);
+ * writes the row-major image int32[h][w] to out_pix_dev. */
+int ray_b200_detile(struct futhark_context *ctx, const int32_t *gathered_dev, int32_t *out_pix_dev, int64_t h,
+                    int64_t w, int32_t world);
+
+/* ---- work counters (roofline numerators) ---------------------------------------------------------- */
+struct ray_b200_counters { uint64_t segments, node_steps, box_tests, leaf_tests; };
+/* Re-renders (1 spp) with counting kernels and returns the work the GPU traversal did. */
+int ray_b200_count_work(struct futhark_context *ctx, int64_t h, int64_t w, int32_t spp,
+                        const struct futhark_opaque_prepared_scene *p, struct ray_b200_counters *out);
+
+/* ---- host-only entry points (no context, no device needed): the setup path's host logic ------------ */
+/* name: "rgbbox" | "irreg" | "random" (n, seed used by "random" only).  spheres may be NULL to query *count. */
+int ray_b200_host_scene(const char *name, int64_t n, uint64_t seed, float *spheres, int64_t capacity, float *cam7,
+                        int64_t *count);
+/* camera look_from look_at (0,1,0) fov (w/h)  (ray.fut:93-107, 243-244) -> origin, llc, horizontal, vertical */
+int ray_b200_host_camera(const float *cam7, int64_t h, int64_t w, float *out12);
+/* bvh_mk (bvh.fut:30-59) in Karras order; info4 = {refit_sweeps, max_depth, stale_nodes, 0}. 2 = n < 2. */
+int ray_b200_host_lbvh(const float *spheres, int64_t n, uint32_t *morton, int32_t *perm, int32_t *left,
+                       int32_t *right, int32_t *parent, float *boxes, int32_t *info4);
+void ray_b200_host_sample_offsets(int32_t spp, float *table);
+
+const char *ray_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAY_B200_EXT_H */

@@ -1,0 +1,799 @@
+// C ABI of libray_b200.so: the Futhark-compatible surface of include/ray.h (what futhark/main.c links
+// against) plus the extensions of include/ray_b200.h.  No CPU fallback: without a usable CUDA device
+// futhark_context_new reports an error and every entry point fails.
+#include "../../include/ray_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "render_params.h"
+#include "scene_host.h"
+
+using namespace rayb200;
+
+// ------------------------------------------------------------------------------------------ objects
+struct futhark_context_config {
+  int device = 0;
+  int debugging = 0, profiling = 0, logging = 0;
+  int32_t spp = 1;
+  int32_t kernel = RAY_B200_KERNEL_AUTO;
+  int32_t rank = 0, world = 1;
+  int32_t block_threads = 256, blocks_per_sm = 2, smem_budget = 64 * 1024, refill_min = 8;
+  std::string cache_file;
+};
+
+struct futhark_context {
+  futhark_context_config cfg;
+  std::mutex mu;
+  char *error = nullptr;
+  FILE *log = stderr;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+  bool have_timing = false;
+  int sm_count = 0, max_smem_optin = 0;
+  int32_t *work_cursor = nullptr;           // device
+  unsigned long long *counters = nullptr;   // device [4]
+  float *offsets = nullptr;                 // device sample-offset table
+  int32_t offsets_spp = 0;
+  int64_t launches = 0;
+  bool profiling_paused = false;
+  double total_render_ms = 0.0;
+  int64_t renders = 0;
+  bool ok = false;
+};
+
+struct futhark_opaque_scene {
+  HostScene host;
+};
+
+struct futhark_opaque_prepared_scene {
+  HostScene host;   // kept for store/restore
+  int64_t h = 0, w = 0;
+  Lbvh tree;        // Karras-order LBVH (host copy, for introspection and store)
+  CameraRec cam;
+  float root_box[6];
+  int32_t max_depth = 0;
+  float4 *d_nodes = nullptr, *d_geom = nullptr, *d_colour = nullptr;
+  unsigned char *pinned = nullptr;  // packed nodes | geom | colour in page-locked host memory (upload source)
+  size_t nodes_bytes = 0, geom_bytes = 0, colour_bytes = 0;
+  int64_t n = 0;
+};
+
+struct futhark_i32_2d {
+  int32_t *dev = nullptr;
+  int64_t shape[2] = {0, 0};
+  bool owned = true;
+};
+
+// ------------------------------------------------------------------------------------------ helpers
+namespace {
+
+void set_error(futhark_context *ctx, const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  free(ctx->error);
+  ctx->error = strdup(buf);
+  if (ctx->cfg.logging || ctx->cfg.debugging) fprintf(ctx->log ? ctx->log : stderr, "[ray_b200] error: %s\n", buf);
+}
+
+#define CUDA_TRY(ctx, call)                                                                     \
+  do {                                                                                          \
+    cudaError_t e_ = (call);                                                                    \
+    if (e_ != cudaSuccess) {                                                                    \
+      set_error(ctx, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      return 1;                                                                                 \
+    }                                                                                           \
+  } while (0)
+
+int env_int(const char *name, int dflt) {
+  const char *v = getenv(name);
+  if (!v || !*v) return dflt;
+  return atoi(v);
+}
+
+int parse_kernel(const char *v, int dflt) {
+  if (!v || !*v) return dflt;
+  if (!strcmp(v, "auto")) return RAY_B200_KERNEL_AUTO;
+  if (!strcmp(v, "mega")) return RAY_B200_KERNEL_MEGA;
+  if (!strcmp(v, "persistent")) return RAY_B200_KERNEL_PERSISTENT;
+  if (!strcmp(v, "wavefront")) return RAY_B200_KERNEL_WAVEFRONT;
+  return atoi(v);
+}
+
+const char *kTuningNames[] = {"kernel", "spp", "blocks_per_sm", "smem_budget", "refill_min", "rank", "world"};
+constexpr int kNumTuning = sizeof(kTuningNames) / sizeof(kTuningNames[0]);
+
+bool bad_ctx(futhark_context *ctx) { return ctx == nullptr || !ctx->ok; }
+
+int ensure_offsets(futhark_context *ctx, int32_t spp) {
+  if (ctx->offsets && ctx->offsets_spp == spp) return 0;
+  std::vector<float> table;
+  sample_offsets(spp, table);
+  if (ctx->offsets) CUDA_TRY(ctx, cudaFree(ctx->offsets));
+  ctx->offsets = nullptr;
+  CUDA_TRY(ctx, cudaMalloc(&ctx->offsets, table.size() * sizeof(float)));
+  CUDA_TRY(ctx, cudaMemcpy(ctx->offsets, table.data(), table.size() * sizeof(float), cudaMemcpyHostToDevice));
+  ctx->offsets_spp = spp;
+  return 0;
+}
+
+int64_t tiles_total(int64_t h, int64_t w) { return ((h + kTileH - 1) / kTileH) * ((w + kTileW - 1) / kTileW); }
+int64_t tiles_of_rank(int64_t h, int64_t w, int32_t rank, int32_t world) {
+  const int64_t t = tiles_total(h, w);
+  return t / world + ((t % world) > rank ? 1 : 0);
+}
+
+// Fills the kernel parameter block for one frame.
+int fill_params(futhark_context *ctx, const futhark_opaque_prepared_scene *p, int64_t h, int64_t w, int32_t spp,
+                int32_t rank, int32_t world, int32_t *out_pix, float *out_rgb, bool tile_major, RenderParams &P) {
+  if (!p || !p->d_nodes) { set_error(ctx, "render: invalid prepared scene"); return 1; }
+  if (h <= 0 || w <= 0 || h > 65536 || w > 65536) { set_error(ctx, "render: bad image size %lldx%lld", (long long)h, (long long)w); return 1; }
+  if (spp < 1) { set_error(ctx, "render: spp must be >= 1"); return 1; }
+  if (world < 1 || rank < 0 || rank >= world) { set_error(ctx, "render: bad shard %d/%d", rank, world); return 1; }
+  if (p->max_depth > kStackSize - 1) { set_error(ctx, "render: BVH depth %d exceeds the traversal stack", p->max_depth); return 1; }
+  if (ensure_offsets(ctx, spp)) return 1;
+  memset(&P, 0, sizeof P);
+  P.nodes = p->d_nodes; P.geom = p->d_geom; P.colour = p->d_colour;
+  P.n_inner = (int32_t)(p->n - 1); P.n_leaves = (int32_t)p->n;
+  memcpy(P.root_box, p->root_box, sizeof P.root_box);
+  // The camera depends on the aspect ratio w/h given to prepare_scene (ray.fut:243-244); render's own
+  // h, w only set the pixel grid (ray.fut:246-247) — exactly as in the reference.
+  memcpy(P.cam, &p->cam, sizeof P.cam);
+  P.W = (int32_t)w; P.H = (int32_t)h; P.spp = spp; P.inv_spp = 1.0f / (float)spp;
+  P.offsets = ctx->offsets;
+  P.out_pix = out_pix; P.out_rgb = out_rgb; P.tile_major = tile_major ? 1 : 0;
+  P.rank = rank; P.world = world;
+  P.tiles_x = (int32_t)((w + kTileW - 1) / kTileW); P.tiles_y = (int32_t)((h + kTileH - 1) / kTileH);
+  P.n_tiles = tiles_total(h, w);
+  P.local_tiles = tiles_of_rank(h, w, rank, world);
+  P.work_cursor = ctx->work_cursor;
+  P.counters = ctx->counters;
+  // shared-memory staging plan: BFS prefix of the node array, then the sphere records if they all fit
+  const int64_t budget = std::min<int64_t>(ctx->cfg.smem_budget, ctx->max_smem_optin - 1024) - 128;
+  int64_t nodes_fit = std::max<int64_t>(0, budget / 64);
+  P.smem_nodes = (int32_t)std::min<int64_t>(P.n_inner, nodes_fit);
+  const int64_t left = budget - (int64_t)P.smem_nodes * 64;
+  P.smem_spheres = (P.smem_nodes == P.n_inner && left >= (int64_t)P.n_leaves * 16) ? P.n_leaves : 0;
+  return 0;
+}
+
+int resolve_kernel(const futhark_context *ctx) {
+  int k = ctx->cfg.kernel;
+  if (k == RAY_B200_KERNEL_AUTO) k = RAY_B200_KERNEL_PERSISTENT;
+  if (k == RAY_B200_KERNEL_WAVEFRONT) k = RAY_B200_KERNEL_PERSISTENT;  // TODO(wavefront): falls back until K2 lands
+  return k;
+}
+
+int do_render(futhark_context *ctx, const RenderParams &P) {
+  LaunchConfig lc;
+  lc.kernel = resolve_kernel(ctx);
+  lc.block_threads = ctx->cfg.block_threads;
+  lc.blocks_per_sm = ctx->cfg.blocks_per_sm;
+  lc.sm_count = ctx->sm_count;
+  lc.smem_budget = ctx->cfg.smem_budget;
+  lc.refill_min = ctx->cfg.refill_min;
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev_start, ctx->stream));
+  if (lc.kernel != RAY_B200_KERNEL_MEGA) CUDA_TRY(ctx, cudaMemsetAsync(ctx->work_cursor, 0, sizeof(int32_t), ctx->stream));
+  launch_render(P, lc, nullptr, ctx->stream, &ctx->launches);
+  CUDA_TRY(ctx, cudaGetLastError());
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev_stop, ctx->stream));
+  ctx->have_timing = true;
+  ctx->renders++;
+  return 0;
+}
+
+void free_prepared_device(futhark_opaque_prepared_scene *p) {
+  if (p->d_nodes) cudaFree(p->d_nodes);
+  if (p->d_geom) cudaFree(p->d_geom);
+  if (p->d_colour) cudaFree(p->d_colour);
+  if (p->pinned) cudaFreeHost(p->pinned);
+  p->d_nodes = p->d_geom = p->d_colour = nullptr;
+  p->pinned = nullptr;
+}
+
+// Host -> device copy of the packed scene from page-locked memory (asynchronous on the context stream).
+int copy_prepared_h2d(futhark_context *ctx, futhark_opaque_prepared_scene *p) {
+  CUDA_TRY(ctx, cudaMemcpyAsync(p->d_nodes, p->pinned, p->nodes_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(p->d_geom, p->pinned + p->nodes_bytes, p->geom_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(p->d_colour, p->pinned + p->nodes_bytes + p->geom_bytes, p->colour_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return 0;
+}
+
+int upload_prepared(futhark_context *ctx, futhark_opaque_prepared_scene *p) {
+  PackedBvh pk;
+  pack_bvh(p->host, p->tree, pk);
+  memcpy(p->root_box, pk.root_box, sizeof p->root_box);
+  p->max_depth = pk.max_depth;
+  p->n = p->tree.n;
+  p->nodes_bytes = pk.nodes.size() * sizeof(F4);
+  p->geom_bytes = pk.geom.size() * sizeof(F4);
+  p->colour_bytes = pk.colour.size() * sizeof(F4);
+  CUDA_TRY(ctx, cudaMallocHost(&p->pinned, p->nodes_bytes + p->geom_bytes + p->colour_bytes));
+  memcpy(p->pinned, pk.nodes.data(), p->nodes_bytes);
+  memcpy(p->pinned + p->nodes_bytes, pk.geom.data(), p->geom_bytes);
+  memcpy(p->pinned + p->nodes_bytes + p->geom_bytes, pk.colour.data(), p->colour_bytes);
+  CUDA_TRY(ctx, cudaMalloc(&p->d_nodes, p->nodes_bytes));
+  CUDA_TRY(ctx, cudaMalloc(&p->d_geom, p->geom_bytes));
+  CUDA_TRY(ctx, cudaMalloc(&p->d_colour, p->colour_bytes));
+  return copy_prepared_h2d(ctx, p);  // completion: futhark_context_sync, or stream order for later renders
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------ config / context
+extern "C" {
+
+struct futhark_context_config *futhark_context_config_new(void) {
+  futhark_context_config *cfg = new (std::nothrow) futhark_context_config;
+  return cfg;
+}
+void futhark_context_config_free(struct futhark_context_config *cfg) { delete cfg; }
+void futhark_context_config_set_debugging(struct futhark_context_config *cfg, int flag) { cfg->debugging = flag; }
+void futhark_context_config_set_profiling(struct futhark_context_config *cfg, int flag) { cfg->profiling = flag; }
+void futhark_context_config_set_logging(struct futhark_context_config *cfg, int flag) { cfg->logging = flag; }
+void futhark_context_config_set_cache_file(struct futhark_context_config *cfg, const char *f) { cfg->cache_file = f ? f : ""; }
+void futhark_context_config_set_device(struct futhark_context_config *cfg, const char *s) {
+  if (!s) return;
+  if (*s == '#') s++;
+  cfg->device = atoi(s);
+}
+int futhark_get_tuning_param_count(void) { return kNumTuning; }
+const char *futhark_get_tuning_param_name(int i) { return (i >= 0 && i < kNumTuning) ? kTuningNames[i] : nullptr; }
+const char *futhark_get_tuning_param_class(int i) { return (i >= 0 && i < kNumTuning) ? "ray_b200" : nullptr; }
+int futhark_context_config_set_tuning_param(struct futhark_context_config *cfg, const char *name, size_t v) {
+  if (!strcmp(name, "kernel")) cfg->kernel = (int32_t)v;
+  else if (!strcmp(name, "spp")) cfg->spp = (int32_t)v;
+  else if (!strcmp(name, "blocks_per_sm")) cfg->blocks_per_sm = (int32_t)v;
+  else if (!strcmp(name, "smem_budget")) cfg->smem_budget = (int32_t)v;
+  else if (!strcmp(name, "refill_min")) cfg->refill_min = (int32_t)v;
+  else if (!strcmp(name, "rank")) cfg->rank = (int32_t)v;
+  else if (!strcmp(name, "world")) cfg->world = (int32_t)v;
+  else return 1;
+  return 0;
+}
+
+struct futhark_context *futhark_context_new(struct futhark_context_config *cfg) {
+  futhark_context *ctx = new (std::nothrow) futhark_context;
+  if (!ctx) return nullptr;
+  if (cfg) ctx->cfg = *cfg;
+  // environment overrides: the only extension channel an unmodified futhark/main.c has
+  ctx->cfg.device = env_int("RAY_DEVICE", ctx->cfg.device);
+  ctx->cfg.spp = env_int("RAY_SPP", ctx->cfg.spp);
+  ctx->cfg.kernel = parse_kernel(getenv("RAY_KERNEL"), ctx->cfg.kernel);
+  ctx->cfg.rank = env_int("RAY_RANK", ctx->cfg.rank);
+  ctx->cfg.world = env_int("RAY_WORLD", ctx->cfg.world);
+  ctx->cfg.blocks_per_sm = env_int("RAY_BLOCKS_PER_SM", ctx->cfg.blocks_per_sm);
+  ctx->cfg.smem_budget = env_int("RAY_SMEM_BUDGET", ctx->cfg.smem_budget);
+  ctx->cfg.refill_min = env_int("RAY_REFILL_MIN", ctx->cfg.refill_min);
+
+  auto fail = [&](const char *what, cudaError_t e) {
+    set_error(ctx, "futhark_context_new: %s: %s (this library has no CPU fallback)", what, cudaGetErrorString(e));
+    return ctx;
+  };
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return fail("no CUDA device", e == cudaSuccess ? cudaErrorNoDevice : e);
+  if (ctx->cfg.device < 0 || ctx->cfg.device >= ndev) return fail("device index out of range", cudaErrorInvalidDevice);
+  if ((e = cudaSetDevice(ctx->cfg.device)) != cudaSuccess) return fail("cudaSetDevice", e);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, ctx->cfg.device)) != cudaSuccess) return fail("cudaGetDeviceProperties", e);
+  if (prop.major < 10) {
+    set_error(ctx, "futhark_context_new: device %d is sm_%d%d; this library is built for sm_100a (B200) only",
+              ctx->cfg.device, prop.major, prop.minor);
+    return ctx;
+  }
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+  ctx->stream = ctx->own_stream;
+  if ((e = cudaEventCreate(&ctx->ev_start)) != cudaSuccess) return fail("cudaEventCreate", e);
+  if ((e = cudaEventCreate(&ctx->ev_stop)) != cudaSuccess) return fail("cudaEventCreate", e);
+  if ((e = cudaMalloc(&ctx->work_cursor, 64)) != cudaSuccess) return fail("cudaMalloc", e);
+  if ((e = cudaMalloc(&ctx->counters, 4 * sizeof(unsigned long long))) != cudaSuccess) return fail("cudaMalloc", e);
+  if ((e = configure_kernels(ctx->max_smem_optin)) != cudaSuccess) return fail("cudaFuncSetAttribute", e);
+  // keep freed frames in the stream-ordered pool: futhark/main.c frees and re-allocates the image every run
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, ctx->cfg.device) == cudaSuccess) {
+    unsigned long long keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  ctx->ok = true;
+  return ctx;
+}
+
+void futhark_context_free(struct futhark_context *ctx) {
+  if (!ctx) return;
+  if (ctx->ok) {
+    cudaSetDevice(ctx->cfg.device);
+    cudaStreamSynchronize(ctx->stream);
+  }
+  if (ctx->offsets) cudaFree(ctx->offsets);
+  if (ctx->work_cursor) cudaFree(ctx->work_cursor);
+  if (ctx->counters) cudaFree(ctx->counters);
+  if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
+  if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  free(ctx->error);
+  delete ctx;
+}
+
+int futhark_context_sync(struct futhark_context *ctx) {
+  if (bad_ctx(ctx)) return 1;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+char *futhark_context_get_error(struct futhark_context *ctx) {
+  if (!ctx) return nullptr;
+  char *e = ctx->error;
+  ctx->error = nullptr;
+  return e;
+}
+
+char *futhark_context_report(struct futhark_context *ctx) {
+  if (!ctx) return nullptr;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  char buf[512];
+  float ms = 0.0f;
+  if (ctx->ok && ctx->have_timing) {
+    cudaEventSynchronize(ctx->ev_stop);
+    cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_stop);
+  }
+  snprintf(buf, sizeof buf,
+           "ray_b200 %s\ndevice: %d (%d SMs)\nrenders: %lld\nkernel launches: %lld\nlast render: %.3f ms (device)\n",
+           ray_b200_version(), ctx->cfg.device, ctx->sm_count, (long long)ctx->renders, (long long)ctx->launches, ms);
+  return strdup(buf);
+}
+void futhark_context_set_logging_file(struct futhark_context *ctx, FILE *f) { if (ctx) ctx->log = f; }
+void futhark_context_pause_profiling(struct futhark_context *ctx) { if (ctx) ctx->profiling_paused = true; }
+void futhark_context_unpause_profiling(struct futhark_context *ctx) { if (ctx) ctx->profiling_paused = false; }
+int futhark_context_clear_caches(struct futhark_context *ctx) {
+  if (bad_ctx(ctx)) return 1;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  cudaMemPool_t pool;
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (cudaDeviceGetDefaultMemPool(&pool, ctx->cfg.device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ arrays
+struct futhark_i32_2d *futhark_new_i32_2d(struct futhark_context *ctx, const int32_t *data, int64_t d0, int64_t d1) {
+  if (bad_ctx(ctx) || d0 < 0 || d1 < 0) return nullptr;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  futhark_i32_2d *a = new futhark_i32_2d;
+  a->shape[0] = d0; a->shape[1] = d1;
+  const size_t bytes = (size_t)d0 * d1 * sizeof(int32_t);
+  if (cudaMallocAsync(&a->dev, bytes ? bytes : 4, ctx->stream) != cudaSuccess) { set_error(ctx, "futhark_new_i32_2d: out of device memory"); delete a; return nullptr; }
+  if (bytes && cudaMemcpyAsync(a->dev, data, bytes, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { set_error(ctx, "futhark_new_i32_2d: copy failed"); cudaFreeAsync(a->dev, ctx->stream); delete a; return nullptr; }
+  cudaStreamSynchronize(ctx->stream);
+  return a;
+}
+struct futhark_i32_2d *futhark_new_raw_i32_2d(struct futhark_context *ctx, void *device_ptr, int64_t d0, int64_t d1) {
+  if (bad_ctx(ctx)) return nullptr;
+  futhark_i32_2d *a = new futhark_i32_2d;
+  a->dev = (int32_t *)device_ptr; a->shape[0] = d0; a->shape[1] = d1; a->owned = false;
+  return a;
+}
+int futhark_free_i32_2d(struct futhark_context *ctx, struct futhark_i32_2d *arr) {
+  if (bad_ctx(ctx)) return 1;
+  if (!arr) return 0;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (arr->owned && arr->dev) CUDA_TRY(ctx, cudaFreeAsync(arr->dev, ctx->stream));
+  delete arr;
+  return 0;
+}
+int futhark_values_i32_2d(struct futhark_context *ctx, struct futhark_i32_2d *arr, int32_t *data) {
+  if (bad_ctx(ctx)) return 1;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (!arr || !data) { set_error(ctx, "futhark_values_i32_2d: null argument"); return 1; }
+  const size_t bytes = (size_t)arr->shape[0] * arr->shape[1] * sizeof(int32_t);
+  CUDA_TRY(ctx, cudaMemcpyAsync(data, arr->dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // main.c:130-133 reads `data` without syncing
+  return 0;
+}
+void *futhark_values_raw_i32_2d(struct futhark_context *ctx, struct futhark_i32_2d *arr) { (void)ctx; return arr ? arr->dev : nullptr; }
+const int64_t *futhark_shape_i32_2d(struct futhark_context *ctx, struct futhark_i32_2d *arr) { (void)ctx; return arr ? arr->shape : nullptr; }
+
+// ------------------------------------------------------------------------------------------ opaque scene
+int futhark_free_opaque_scene(struct futhark_context *ctx, struct futhark_opaque_scene *obj) { (void)ctx; delete obj; return 0; }
+
+namespace {
+constexpr uint32_t kSceneMagic = 0x53423252u;     // "R2BS"
+constexpr uint32_t kPreparedMagic = 0x50423252u;  // "R2BP"
+size_t scene_blob_size(const HostScene &s) { return 16 + 7 * sizeof(float) + s.spheres.size() * sizeof(SphereRec); }
+void scene_to_blob(const HostScene &s, unsigned char *p, uint32_t magic) {
+  const uint64_t n = s.spheres.size();
+  memcpy(p, &magic, 4); uint32_t ver = 1; memcpy(p + 4, &ver, 4); memcpy(p + 8, &n, 8);
+  float cam[7] = {s.look_from[0], s.look_from[1], s.look_from[2], s.look_at[0], s.look_at[1], s.look_at[2], s.fov};
+  memcpy(p + 16, cam, sizeof cam);
+  memcpy(p + 16 + sizeof cam, s.spheres.data(), n * sizeof(SphereRec));
+}
+bool scene_from_blob(HostScene &s, const unsigned char *p, uint32_t magic) {
+  uint32_t m, ver; uint64_t n;
+  memcpy(&m, p, 4); memcpy(&ver, p + 4, 4); memcpy(&n, p + 8, 8);
+  if (m != magic || ver != 1) return false;
+  float cam[7];
+  memcpy(cam, p + 16, sizeof cam);
+  memcpy(s.look_from, cam, 12); memcpy(s.look_at, cam + 3, 12); s.fov = cam[6];
+  s.spheres.resize(n);
+  memcpy(s.spheres.data(), p + 16 + sizeof cam, n * sizeof(SphereRec));
+  return true;
+}
+}  // namespace
+
+int futhark_store_opaque_scene(struct futhark_context *ctx, const struct futhark_opaque_scene *obj, void **p, size_t *n) {
+  if (!ctx || !obj || !n) return 1;
+  const size_t sz = scene_blob_size(obj->host);
+  *n = sz;
+  if (p) {
+    if (!*p) *p = malloc(sz);
+    if (!*p) { set_error(ctx, "store_opaque_scene: out of memory"); return 1; }
+    scene_to_blob(obj->host, (unsigned char *)*p, kSceneMagic);
+  }
+  return 0;
+}
+struct futhark_opaque_scene *futhark_restore_opaque_scene(struct futhark_context *ctx, const void *p) {
+  if (!ctx || !p) return nullptr;
+  futhark_opaque_scene *s = new futhark_opaque_scene;
+  if (!scene_from_blob(s->host, (const unsigned char *)p, kSceneMagic)) { set_error(ctx, "restore_opaque_scene: bad blob"); delete s; return nullptr; }
+  return s;
+}
+
+int futhark_free_opaque_prepared_scene(struct futhark_context *ctx, struct futhark_opaque_prepared_scene *obj) {
+  if (!obj) return 0;
+  if (ctx && ctx->ok) {
+    std::lock_guard<std::mutex> g(ctx->mu);
+    cudaStreamSynchronize(ctx->stream);  // a render using it may still be in flight
+    free_prepared_device(obj);
+  }
+  delete obj;
+  return 0;
+}
+// A stored prepared scene is the scene plus the (h, w) it was prepared for; restoring re-runs prepare_scene.
+int futhark_store_opaque_prepared_scene(struct futhark_context *ctx, const struct futhark_opaque_prepared_scene *obj, void **p, size_t *n) {
+  if (!ctx || !obj || !n) return 1;
+  const size_t sz = scene_blob_size(obj->host) + 16;
+  *n = sz;
+  if (p) {
+    if (!*p) *p = malloc(sz);
+    if (!*p) { set_error(ctx, "store_opaque_prepared_scene: out of memory"); return 1; }
+    scene_to_blob(obj->host, (unsigned char *)*p, kPreparedMagic);
+    memcpy((unsigned char *)*p + sz - 16, &obj->h, 8);
+    memcpy((unsigned char *)*p + sz - 8, &obj->w, 8);
+  }
+  return 0;
+}
+struct futhark_opaque_prepared_scene *futhark_restore_opaque_prepared_scene(struct futhark_context *ctx, const void *p) {
+  if (bad_ctx(ctx) || !p) return nullptr;
+  futhark_opaque_scene tmp;
+  if (!scene_from_blob(tmp.host, (const unsigned char *)p, kPreparedMagic)) { set_error(ctx, "restore_opaque_prepared_scene: bad blob"); return nullptr; }
+  const size_t sz = scene_blob_size(tmp.host) + 16;
+  int64_t h, w;
+  memcpy(&h, (const unsigned char *)p + sz - 16, 8);
+  memcpy(&w, (const unsigned char *)p + sz - 8, 8);
+  futhark_opaque_prepared_scene *out = nullptr;
+  if (futhark_entry_prepare_scene(ctx, &out, h, w, &tmp) != 0) return nullptr;
+  return out;
+}
+
+// ------------------------------------------------------------------------------------------ entry points
+int futhark_entry_rgbbox(struct futhark_context *ctx, struct futhark_opaque_scene **out0) {
+  if (bad_ctx(ctx) || !out0) return 1;
+  futhark_opaque_scene *s = new futhark_opaque_scene;
+  make_rgbbox(s->host);
+  *out0 = s;
+  return 0;
+}
+int futhark_entry_irreg(struct futhark_context *ctx, struct futhark_opaque_scene **out0) {
+  if (bad_ctx(ctx) || !out0) return 1;
+  futhark_opaque_scene *s = new futhark_opaque_scene;
+  make_irreg(s->host);
+  *out0 = s;
+  return 0;
+}
+
+int futhark_entry_prepare_scene(struct futhark_context *ctx, struct futhark_opaque_prepared_scene **out0, const int64_t h,
+                                const int64_t w, const struct futhark_opaque_scene *scene) {
+  if (bad_ctx(ctx)) return 1;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (!out0 || !scene) { set_error(ctx, "prepare_scene: null argument"); return 1; }
+  if (h <= 0 || w <= 0) { set_error(ctx, "prepare_scene: bad image size"); return 1; }
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  futhark_opaque_prepared_scene *p = new futhark_opaque_prepared_scene;
+  p->host = scene->host;
+  p->h = h; p->w = w;
+  std::string err;
+  if (!build_lbvh(p->host, p->tree, &err)) { set_error(ctx, "%s", err.c_str()); delete p; return 1; }
+  p->cam = make_camera(p->host, h, w);
+  if (upload_prepared(ctx, p)) { free_prepared_device(p); delete p; return 1; }
+  *out0 = p;
+  return 0;
+}
+
+int ray_b200_entry_render_spp(struct futhark_context *ctx, struct futhark_i32_2d **out0, int64_t h, int64_t w, int32_t spp,
+                              const struct futhark_opaque_prepared_scene *p) {
+  if (bad_ctx(ctx)) return 1;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (!out0) { set_error(ctx, "render: null output"); return 1; }
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  futhark_i32_2d *img = new futhark_i32_2d;
+  img->shape[0] = h; img->shape[1] = w;
+  const size_t bytes = (size_t)(h > 0 ? h : 0) * (size_t)(w > 0 ? w : 0) * sizeof(int32_t);
+  cudaError_t e = cudaMallocAsync(&img->dev, bytes ? bytes : 4, ctx->stream);
+  if (e != cudaSuccess) { set_error(ctx, "render: cudaMallocAsync: %s", cudaGetErrorString(e)); delete img; return 1; }
+  RenderParams P;
+  // With a shard configured, the row-major frame only receives this rank's tiles; clear the rest.
+  if (ctx->cfg.world > 1) cudaMemsetAsync(img->dev, 0, bytes, ctx->stream);
+  if (fill_params(ctx, p, h, w, spp, ctx->cfg.rank, ctx->cfg.world, img->dev, nullptr, false, P) || do_render(ctx, P)) {
+    cudaFreeAsync(img->dev, ctx->stream);
+    delete img;
+    return 1;
+  }
+  *out0 = img;
+  return 0;
+}
+
+int futhark_entry_render(struct futhark_context *ctx, struct futhark_i32_2d **out0, const int64_t h, const int64_t w,
+                         const struct futhark_opaque_prepared_scene *p) {
+  if (bad_ctx(ctx)) return 1;
+  return ray_b200_entry_render_spp(ctx, out0, h, w, ctx->cfg.spp, p);
+}
+
+// ------------------------------------------------------------------------------------------ extensions
+int ray_b200_context_set_stream(struct futhark_context *ctx, void *s) {
+  if (bad_ctx(ctx)) return 1;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+  return 0;
+}
+int ray_b200_context_set_spp(struct futhark_context *ctx, int32_t spp) {
+  if (bad_ctx(ctx)) return 1;
+  if (spp < 1) { set_error(ctx, "spp must be >= 1"); return 1; }
+  ctx->cfg.spp = spp;
+  return 0;
+}
+int ray_b200_context_set_kernel(struct futhark_context *ctx, int32_t k) {
+  if (bad_ctx(ctx)) return 1;
+  if (k < RAY_B200_KERNEL_AUTO || k > RAY_B200_KERNEL_WAVEFRONT) { set_error(ctx, "unknown kernel %d", k); return 1; }
+  ctx->cfg.kernel = k;
+  return 0;
+}
+int ray_b200_context_set_shard(struct futhark_context *ctx, int32_t rank, int32_t world) {
+  if (bad_ctx(ctx)) return 1;
+  if (world < 1 || rank < 0 || rank >= world) { set_error(ctx, "bad shard %d/%d", rank, world); return 1; }
+  ctx->cfg.rank = rank; ctx->cfg.world = world;
+  return 0;
+}
+int ray_b200_context_device(struct futhark_context *ctx) { return ctx ? ctx->cfg.device : -1; }
+int ray_b200_context_last_render_ms(struct futhark_context *ctx, float *ms) {
+  if (bad_ctx(ctx) || !ms) return 1;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (!ctx->have_timing) { set_error(ctx, "no render has been issued yet"); return 1; }
+  CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev_stop));
+  CUDA_TRY(ctx, cudaEventElapsedTime(ms, ctx->ev_start, ctx->ev_stop));
+  return 0;
+}
+int64_t ray_b200_context_launch_count(struct futhark_context *ctx) { return ctx ? ctx->launches : 0; }
+
+int ray_b200_scene_from_arrays(struct futhark_context *ctx, struct futhark_opaque_scene **out0, const float *spheres, int64_t n,
+                               const float *cam7) {
+  if (bad_ctx(ctx)) return 1;
+  if (!out0 || !spheres || !cam7 || n < 0) { set_error(ctx, "scene_from_arrays: bad argument"); return 1; }
+  futhark_opaque_scene *s = new futhark_opaque_scene;
+  s->host.spheres.resize((size_t)n);
+  static_assert(sizeof(SphereRec) == 7 * sizeof(float), "SphereRec must be 7 packed floats");
+  memcpy(s->host.spheres.data(), spheres, (size_t)n * sizeof(SphereRec));
+  memcpy(s->host.look_from, cam7, 12); memcpy(s->host.look_at, cam7 + 3, 12); s->host.fov = cam7[6];
+  *out0 = s;
+  return 0;
+}
+int ray_b200_scene_random(struct futhark_context *ctx, struct futhark_opaque_scene **out0, int64_t n, uint64_t seed) {
+  if (bad_ctx(ctx)) return 1;
+  if (!out0 || n < 0) { set_error(ctx, "scene_random: bad argument"); return 1; }
+  futhark_opaque_scene *s = new futhark_opaque_scene;
+  make_random(s->host, n, seed);
+  *out0 = s;
+  return 0;
+}
+int64_t ray_b200_scene_num_spheres(struct futhark_context *ctx, const struct futhark_opaque_scene *s) { (void)ctx; return s ? (int64_t)s->host.spheres.size() : -1; }
+int ray_b200_scene_get_arrays(struct futhark_context *ctx, const struct futhark_opaque_scene *s, float *spheres, float *cam7) {
+  (void)ctx;
+  if (!s) return 1;
+  if (spheres) memcpy(spheres, s->host.spheres.data(), s->host.spheres.size() * sizeof(SphereRec));
+  if (cam7) { memcpy(cam7, s->host.look_from, 12); memcpy(cam7 + 3, s->host.look_at, 12); cam7[6] = s->host.fov; }
+  return 0;
+}
+
+int ray_b200_prepared_info(struct futhark_context *ctx, const struct futhark_opaque_prepared_scene *p, struct ray_b200_bvh_info *info) {
+  if (bad_ctx(ctx) || !p || !info) return 1;
+  memset(info, 0, sizeof *info);
+  info->n_leaves = p->n; info->n_inner = p->n - 1;
+  info->max_depth = p->tree.max_depth; info->refit_sweeps = p->tree.refit_sweeps; info->stale_nodes = p->tree.stale_nodes;
+  RenderParams P;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (fill_params(ctx, p, 8, 8, 1, 0, 1, nullptr, nullptr, false, P) == 0) info->smem_nodes = P.smem_nodes;
+  memcpy(info->root_box, p->root_box, sizeof info->root_box);
+  memcpy(info->camera, &p->cam, sizeof info->camera);
+  return 0;
+}
+int ray_b200_prepared_dump(struct futhark_context *ctx, const struct futhark_opaque_prepared_scene *p, uint32_t *morton, int32_t *perm,
+                           int32_t *left, int32_t *right, int32_t *parent, float *boxes) {
+  (void)ctx;
+  if (!p) return 1;
+  const Lbvh &t = p->tree;
+  if (morton) memcpy(morton, t.morton.data(), t.morton.size() * 4);
+  if (perm) memcpy(perm, t.perm.data(), t.perm.size() * 4);
+  if (left) memcpy(left, t.left.data(), t.left.size() * 4);
+  if (right) memcpy(right, t.right.data(), t.right.size() * 4);
+  if (parent) memcpy(parent, t.parent.data(), t.parent.size() * 4);
+  if (boxes) memcpy(boxes, t.boxes.data(), t.boxes.size() * 4);
+  return 0;
+}
+
+int ray_b200_prepared_reupload(struct futhark_context *ctx, struct futhark_opaque_prepared_scene *p) {
+  if (bad_ctx(ctx)) return 1;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (!p || !p->pinned) { set_error(ctx, "prepared_reupload: invalid prepared scene"); return 1; }
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  return copy_prepared_h2d(ctx, p);
+}
+int64_t ray_b200_prepared_device_bytes(struct futhark_context *ctx, const struct futhark_opaque_prepared_scene *p) {
+  (void)ctx;
+  return p ? (int64_t)(p->nodes_bytes + p->geom_bytes + p->colour_bytes) : -1;
+}
+
+int ray_b200_render_into(struct futhark_context *ctx, int32_t *out_pix_dev, float *out_rgb_dev, int64_t h, int64_t w, int32_t spp,
+                         const struct futhark_opaque_prepared_scene *p) {
+  if (bad_ctx(ctx)) return 1;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (!out_pix_dev) { set_error(ctx, "render_into: out_pix_dev is required"); return 1; }
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  RenderParams P;
+  if (fill_params(ctx, p, h, w, spp, ctx->cfg.rank, ctx->cfg.world, out_pix_dev, out_rgb_dev, false, P)) return 1;
+  return do_render(ctx, P);
+}
+
+int ray_b200_render_host(struct futhark_context *ctx, int32_t *out_pix_host, float *out_rgb_host, int64_t h, int64_t w, int32_t spp,
+                         const struct futhark_opaque_prepared_scene *p) {
+  if (bad_ctx(ctx)) return 1;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (!out_pix_host) { set_error(ctx, "render_host: out_pix_host is required"); return 1; }
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  const size_t px = (size_t)h * (size_t)w;
+  int32_t *d_pix = nullptr;
+  float *d_rgb = nullptr;
+  CUDA_TRY(ctx, cudaMallocAsync(&d_pix, px * 4, ctx->stream));
+  if (out_rgb_host) CUDA_TRY(ctx, cudaMallocAsync(&d_rgb, px * 12, ctx->stream));
+  RenderParams P;
+  int rc = fill_params(ctx, p, h, w, spp, 0, 1, d_pix, d_rgb, false, P) || do_render(ctx, P);
+  if (!rc) {
+    if (cudaMemcpyAsync(out_pix_host, d_pix, px * 4, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) rc = 1;
+    if (!rc && d_rgb && cudaMemcpyAsync(out_rgb_host, d_rgb, px * 12, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) rc = 1;
+    if (rc) set_error(ctx, "render_host: device-to-host copy failed");
+  }
+  cudaFreeAsync(d_pix, ctx->stream);
+  if (d_rgb) cudaFreeAsync(d_rgb, ctx->stream);
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess && !rc) { set_error(ctx, "render_host: kernel failed: %s", cudaGetErrorString(cudaGetLastError())); rc = 1; }
+  return rc;
+}
+
+int64_t ray_b200_shard_tiles(int64_t h, int64_t w, int32_t rank, int32_t world) {
+  if (world < 1 || rank < 0 || rank >= world || h <= 0 || w <= 0) return -1;
+  return tiles_of_rank(h, w, rank, world);
+}
+int64_t ray_b200_shard_tiles_padded(int64_t h, int64_t w, int32_t world) {
+  if (world < 1 || h <= 0 || w <= 0) return -1;
+  return (tiles_total(h, w) + world - 1) / world;
+}
+int ray_b200_render_shard_into(struct futhark_context *ctx, int32_t *out_tiles_dev, int64_t h, int64_t w, int32_t spp,
+                               const struct futhark_opaque_prepared_scene *p) {
+  if (bad_ctx(ctx)) return 1;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (!out_tiles_dev) { set_error(ctx, "render_shard_into: null output"); return 1; }
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  RenderParams P;
+  if (fill_params(ctx, p, h, w, spp, ctx->cfg.rank, ctx->cfg.world, out_tiles_dev, nullptr, true, P)) return 1;
+  // ranks that own one tile fewer than the padded count leave a zeroed tail
+  const int64_t padded = ray_b200_shard_tiles_padded(h, w, ctx->cfg.world);
+  if (P.local_tiles < padded)
+    CUDA_TRY(ctx, cudaMemsetAsync(out_tiles_dev + P.local_tiles * kTilePixels, 0, (size_t)(padded - P.local_tiles) * kTilePixels * 4, ctx->stream));
+  return do_render(ctx, P);
+}
+int ray_b200_detile(struct futhark_context *ctx, const int32_t *gathered_dev, int32_t *out_pix_dev, int64_t h, int64_t w, int32_t world) {
+  if (bad_ctx(ctx)) return 1;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (!gathered_dev || !out_pix_dev || world < 1 || h <= 0 || w <= 0) { set_error(ctx, "detile: bad argument"); return 1; }
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  launch_detile(gathered_dev, out_pix_dev, h, w, world, ray_b200_shard_tiles_padded(h, w, world), ctx->stream, &ctx->launches);
+  CUDA_TRY(ctx, cudaGetLastError());
+  return 0;
+}
+
+int ray_b200_count_work(struct futhark_context *ctx, int64_t h, int64_t w, int32_t spp, const struct futhark_opaque_prepared_scene *p,
+                        struct ray_b200_counters *out) {
+  if (bad_ctx(ctx)) return 1;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (!out) { set_error(ctx, "count_work: null output"); return 1; }
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  int32_t *scratch = nullptr;
+  CUDA_TRY(ctx, cudaMallocAsync(&scratch, (size_t)h * w * 4, ctx->stream));
+  RenderParams P;
+  int rc = fill_params(ctx, p, h, w, spp, 0, 1, scratch, nullptr, false, P);
+  if (!rc) {
+    cudaMemsetAsync(ctx->counters, 0, 4 * sizeof(unsigned long long), ctx->stream);
+    launch_count_work(P, ctx->stream, &ctx->launches);
+    unsigned long long host[4] = {0, 0, 0, 0};
+    if (cudaMemcpyAsync(host, ctx->counters, sizeof host, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+        cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+      set_error(ctx, "count_work: %s", cudaGetErrorString(cudaGetLastError()));
+      rc = 1;
+    }
+    out->segments = host[0]; out->node_steps = host[1]; out->box_tests = host[2]; out->leaf_tests = host[3];
+  }
+  cudaFreeAsync(scratch, ctx->stream);
+  return rc;
+}
+
+// ---- host-only entry points (no context, no device): the setup-path logic, testable without a GPU ----
+int ray_b200_host_scene(const char *name, int64_t n, uint64_t seed, float *spheres, int64_t capacity, float *cam7, int64_t *count) {
+  HostScene s;
+  if (!name) return 1;
+  if (!strcmp(name, "rgbbox")) make_rgbbox(s);
+  else if (!strcmp(name, "irreg")) make_irreg(s);
+  else if (!strcmp(name, "random")) make_random(s, n, seed);
+  else return 1;
+  if (count) *count = (int64_t)s.spheres.size();
+  if (spheres) {
+    if (capacity < (int64_t)s.spheres.size()) return 2;
+    memcpy(spheres, s.spheres.data(), s.spheres.size() * sizeof(SphereRec));
+  }
+  if (cam7) { memcpy(cam7, s.look_from, 12); memcpy(cam7 + 3, s.look_at, 12); cam7[6] = s.fov; }
+  return 0;
+}
+int ray_b200_host_camera(const float *cam7, int64_t h, int64_t w, float *out12) {
+  if (!cam7 || !out12 || h <= 0 || w <= 0) return 1;
+  HostScene s;
+  memcpy(s.look_from, cam7, 12); memcpy(s.look_at, cam7 + 3, 12); s.fov = cam7[6];
+  const CameraRec c = make_camera(s, h, w);
+  memcpy(out12, &c, sizeof c);
+  return 0;
+}
+int ray_b200_host_lbvh(const float *spheres, int64_t n, uint32_t *morton, int32_t *perm, int32_t *left, int32_t *right,
+                       int32_t *parent, float *boxes, int32_t *info4) {
+  if (!spheres || n < 0) return 1;
+  HostScene s;
+  s.spheres.resize((size_t)n);
+  memcpy(s.spheres.data(), spheres, (size_t)n * sizeof(SphereRec));
+  Lbvh t;
+  std::string err;
+  if (!build_lbvh(s, t, &err)) return 2;
+  if (morton) memcpy(morton, t.morton.data(), t.morton.size() * 4);
+  if (perm) memcpy(perm, t.perm.data(), t.perm.size() * 4);
+  if (left) memcpy(left, t.left.data(), t.left.size() * 4);
+  if (right) memcpy(right, t.right.data(), t.right.size() * 4);
+  if (parent) memcpy(parent, t.parent.data(), t.parent.size() * 4);
+  if (boxes) memcpy(boxes, t.boxes.data(), t.boxes.size() * 4);
+  if (info4) { info4[0] = t.refit_sweeps; info4[1] = t.max_depth; info4[2] = t.stale_nodes; info4[3] = 0; }
+  return 0;
+}
+void ray_b200_host_sample_offsets(int32_t spp, float *table) {
+  std::vector<float> t;
+  sample_offsets(spp, t);
+  memcpy(table, t.data(), t.size() * sizeof(float));
+}
+
+const char *ray_b200_version(void) { return "ray_b200 0.1 (sm_100a)"; }
+
+}  // extern "C"

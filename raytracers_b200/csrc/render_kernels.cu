@@ -1,0 +1,433 @@
+// sm_100a render kernels: the reference's per-pixel hot path (ray.fut:126-169 over bvh.fut:61-84)
+// re-designed for B200.  Compiled with -fmad=false; see device_math.cuh for the bit-exactness rules.
+//
+// Traversal.  The reference walks the Karras tree stacklessly (parent pointers, bvh.fut:61-84) and
+// tests every box against the ORIGINAL ray interval (0, 1e9) (ray.fut:77), so the set of leaves it
+// applies `closest_hit` to is exactly { leaf : every ancestor's box passes aabb_hit } — independent
+// of traversal order — and the fold result is the leaf with the smallest accepted t, lowest leaf index
+// on ties (strict `<` at ray.fut:40 with a shrinking t_max, leaves folded in ascending order).  We
+// visit the same set with a left-first stack DFS over the BVH2C layout (scene_host.h): one node step
+// tests both children's boxes, ~half the dependent steps of the reference loop and no re-visits.
+// Left-first DFS also visits leaves in ascending index order, so the strict `<` reproduces the
+// reference's tie-break.
+#include "render_params.h"
+#include "device_math.cuh"
+
+#include <cstdio>
+
+namespace rayb200 {
+
+namespace {
+
+constexpr int kDone = (int)0x80000000;  // traversal sentinel: neither an inner index (>= 0) nor a leaf (~i, i < 2^30)
+constexpr unsigned kFullMask = 0xffffffffu;
+
+struct WorkCounters {
+  unsigned long long segments = 0, node_steps = 0, box_tests = 0, leaf_tests = 0;
+};
+
+// ------------------------------------------------------------------ scene access policies
+struct GlobalScene {  // everything through the read-only path (L1/L2)
+  const float4 *nodes, *geom;
+  __device__ __forceinline__ void node(int cur, float4 &q0, float4 &q1, float4 &q2, float4 &q3) const {
+    const float4 *p = nodes + 4 * (size_t)cur;
+    q0 = __ldg(p); q1 = __ldg(p + 1); q2 = __ldg(p + 2); q3 = __ldg(p + 3);
+  }
+  __device__ __forceinline__ float4 sphere(int i) const { return __ldg(geom + i); }
+};
+
+template <bool kAllNodes, bool kSpheres>
+struct StagedScene {  // top of the tree (BFS prefix) + optionally all spheres in shared memory
+  const float4 *nodes, *geom;
+  const float4 *s_nodes, *s_geom;
+  int smem_nodes;
+  __device__ __forceinline__ void node(int cur, float4 &q0, float4 &q1, float4 &q2, float4 &q3) const {
+    if (kAllNodes || cur < smem_nodes) {
+      const float4 *p = s_nodes + 4 * cur;
+      q0 = p[0]; q1 = p[1]; q2 = p[2]; q3 = p[3];
+    } else {
+      const float4 *p = nodes + 4 * (size_t)cur;
+      q0 = __ldg(p); q1 = __ldg(p + 1); q2 = __ldg(p + 2); q3 = __ldg(p + 3);
+    }
+  }
+  __device__ __forceinline__ float4 sphere(int i) const { return kSpheres ? s_geom[i] : __ldg(geom + i); }
+};
+
+// ------------------------------------------------------------------ objs_hit, first half (ray.fut:76-82)
+// bvh_fold contains closest_hit (-1, 1e9): returns the winning leaf (or -1) and its t.
+template <bool kCount, class Scene>
+__device__ __forceinline__ void find_closest(const Scene &sc, const float *root_box, const Ray &r, const RayInv &q,
+                                             int &best_j, float &best_t, WorkCounters &wc) {
+  best_j = -1;
+  best_t = 1000000000.0f;
+  if (kCount) { wc.segments++; wc.box_tests++; }
+  if (!box_hit(root_box[0], root_box[1], root_box[2], root_box[3], root_box[4], root_box[5], r, q)) return;
+  int stack[kStackSize];
+  int sp = 0;
+  int cur = 0;
+  for (;;) {
+    while (cur >= 0) {  // inner node: test both children's boxes
+      float4 q0, q1, q2, q3;
+      sc.node(cur, q0, q1, q2, q3);
+      const int lptr = __float_as_int(q0.w), rptr = __float_as_int(q1.w);
+      const bool hl = box_hit(q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, r, q);
+      const bool hr = box_hit(q2.x, q2.y, q2.z, q3.x, q3.y, q3.z, r, q);
+      if (kCount) { wc.node_steps++; wc.box_tests += (lptr >= 0) + (rptr >= 0); }
+      if (hl) {
+        if (hr) stack[sp++] = rptr;
+        cur = lptr;
+      } else if (hr) {
+        cur = rptr;
+      } else {
+        cur = sp ? stack[--sp] : kDone;
+      }
+    }
+    if (cur == kDone) break;
+    {  // leaf ~cur: closest_hit (ray.fut:78-81) = sphere_hit s r 0.1 t_best
+      const int li = ~cur;
+      const float4 g = sc.sphere(li);
+      if (kCount) wc.leaf_tests++;
+      const float t = sphere_t(g.x, g.y, g.z, g.w, r, q.a, 0.1f, best_t);
+      if (t >= 0.0f) { best_t = t; best_j = li; }
+    }
+    cur = sp ? stack[--sp] : kDone;
+  }
+}
+
+// ------------------------------------------------------------------ one ray_colour iteration (ray.fut:130-148)
+// Advances the path by one segment.  Returns true if the path continues (r/light updated), false if
+// it ended with `colour` set.  `depth` counts objs_hit calls so far (ray.fut:129).
+template <bool kCount, class Scene>
+__device__ __forceinline__ bool advance_path(const Scene &sc, const RenderParams &P, Ray &r, V3 &light, int &depth,
+                                             V3 &colour, WorkCounters &wc) {
+  const RayInv q = ray_invariants(r);
+  int j;
+  float tb;
+  find_closest<kCount>(sc, P.root_box, r, q, j, tb, wc);
+  if (j >= 0) {
+    // objs_hit, second half (ray.fut:83-85): re-intersect the winner with t_min = 0, t_max = t_best + 1
+    const float4 g = sc.sphere(j);
+    const float t = sphere_t(g.x, g.y, g.z, g.w, r, q.a, 0.0f, tb + 1.0f);
+    if (t >= 0.0f) {
+      const V3 c = v3(g.x, g.y, g.z);
+      const V3 p = vadd(r.o, vscale(t, r.d));                       // point_at_param, ray.fut:14-15
+      const V3 n = vscale(1.0f / g.w, vsub(p, c));                  // ray.fut:42-43
+      // scatter (ray.fut:119-124): reflect (normalise r.dir) hit.normal; norm r.dir = sqrt(dot d d) = sqrt(q.a)
+      const V3 unit = vscale(1.0f / sqrtf(q.a), r.d);
+      const V3 refl = vsub(unit, vscale(2.0f * vdot(unit, n), n));  // ray.fut:116-117
+      if (vdot(refl, n) > 0.0f) {
+        const float4 col = __ldg(P.colour + j);
+        r.o = p;
+        r.d = refl;
+        light = vmul(light, v3(col.x, col.y, col.z));               // ray.fut:135
+        depth = depth + 1;
+        if (depth < kMaxDepth) return true;
+        colour = v3(0.0f, 0.0f, 0.0f);                              // loop exit with colour = light*0 (ray.fut:136)
+        return false;
+      }
+      colour = v3(0.0f, 0.0f, 0.0f);                                // ray.fut:137-140
+      return false;
+    }
+  }
+  // miss: sky gradient (ray.fut:141-148)
+  const V3 unit = vscale(1.0f / sqrtf(q.a), r.d);
+  const float t = 0.5f * (unit.y + 1.0f);
+  const float w1 = 1.0f - t;
+  const V3 sky = v3(w1 * 1.0f + t * 0.5f, w1 * 1.0f + t * 0.7f, w1 * 1.0f + t * 1.0f);
+  colour = vmul(light, sky);
+  return false;
+}
+
+// get_ray for sample s of pixel (row j, column i): ray.fut:150-154 with pixel j i -> trace_ray (height-j) i
+// (ray.fut:167-168) and the spp extension of ray_b200.h (offset (0,0) at s = 0).
+__device__ __forceinline__ Ray primary_ray(const RenderParams &P, int i, int j, int s) {
+  float u, v;
+  if (P.spp == 1) {
+    u = (float)i / (float)P.W;
+    v = (float)(P.H - j) / (float)P.H;
+  } else {
+    u = ((float)i + P.offsets[2 * s]) / (float)P.W;
+    v = ((float)(P.H - j) + P.offsets[2 * s + 1]) / (float)P.H;
+  }
+  const float *c = P.cam;
+  Ray r;
+  r.o = v3(c[0], c[1], c[2]);
+  // llc + s*horizontal + t*vertical - origin (ray.fut:111-113), per component, left to right
+  r.d = v3(((c[3] + u * c[6]) + v * c[9]) - c[0], ((c[4] + u * c[7]) + v * c[10]) - c[1],
+           ((c[5] + u * c[8]) + v * c[11]) - c[2]);
+  return r;
+}
+
+// item k -> pixel.  Local tile lt = k >> 5 is global tile lt*world + rank; lane position k & 31 inside the 8x4 tile.
+__device__ __forceinline__ bool item_pixel(const RenderParams &P, int k, int &i, int &j) {
+  const long long t = (long long)(k >> 5) * P.world + P.rank;
+  const int sub = k & 31;
+  const int ty = (int)(t / P.tiles_x), tx = (int)(t - (long long)ty * P.tiles_x);
+  i = tx * kTileW + (sub & (kTileW - 1));
+  j = ty * kTileH + (sub >> 3);
+  return t < P.n_tiles && i < P.W && j < P.H;
+}
+
+__device__ __forceinline__ void write_pixel(const RenderParams &P, int k, int i, int j, V3 sum) {
+  const V3 col = (P.spp == 1) ? sum : vscale(P.inv_spp, sum);
+  const int pix = pack_pixel(col);
+  if (P.tile_major) P.out_pix[k] = pix;
+  else P.out_pix[(size_t)j * P.W + i] = pix;
+  if (P.out_rgb) {
+    float *q = P.out_rgb + 3 * ((size_t)j * P.W + i);
+    q[0] = col.x; q[1] = col.y; q[2] = col.z;
+  }
+}
+
+__device__ __forceinline__ void flush_counters(const RenderParams &P, WorkCounters &wc) {
+  for (int o = 16; o > 0; o >>= 1) {
+    wc.segments += __shfl_down_sync(kFullMask, wc.segments, o);
+    wc.node_steps += __shfl_down_sync(kFullMask, wc.node_steps, o);
+    wc.box_tests += __shfl_down_sync(kFullMask, wc.box_tests, o);
+    wc.leaf_tests += __shfl_down_sync(kFullMask, wc.leaf_tests, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(P.counters + 0, wc.segments);
+    atomicAdd(P.counters + 1, wc.node_steps);
+    atomicAdd(P.counters + 2, wc.box_tests);
+    atomicAdd(P.counters + 3, wc.leaf_tests);
+  }
+}
+
+// ====================================================================================== K0: megakernel
+// One thread per pixel, the whole ray_colour loop inside (what a Futhark GPU backend would emit,
+// SURVEY.md §8a A11).  The parity anchor and the "naive GPU" number.
+template <bool kCount>
+__global__ void __launch_bounds__(128) render_mega_kernel(const __grid_constant__ RenderParams P) {
+  const long long k64 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  WorkCounters wc;
+  int i = 0, j = 0;
+  const bool valid = k64 < P.local_tiles * kTilePixels && item_pixel(P, (int)k64, i, j);
+  if (valid) {
+    const GlobalScene sc{P.nodes, P.geom};
+    V3 sum = v3(0.0f, 0.0f, 0.0f);
+    for (int s = 0; s < P.spp; s++) {
+      Ray r = primary_ray(P, i, j, s);
+      V3 light = v3(1.0f, 1.0f, 1.0f), colour;
+      int depth = 0;
+      while (advance_path<kCount>(sc, P, r, light, depth, colour, wc)) {}
+      sum = (s == 0) ? colour : vadd(sum, colour);
+    }
+    write_pixel(P, (int)k64, i, j, sum);
+  } else if (P.tile_major && k64 < P.local_tiles * kTilePixels) {
+    P.out_pix[k64] = 0;  // padding pixel of a partial tile
+  }
+  if (kCount) flush_counters(P, wc);
+}
+
+// ====================================================================================== TMA staging helpers
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_addr(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {}
+}
+// 1-D bulk async copy global -> shared through the TMA unit (SASS: UBLKCP), completion on an mbarrier.
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_addr(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+
+// Stages the BFS prefix of the node array (and optionally all sphere records) into shared memory.
+// One elected thread arms the mbarrier with the byte count and issues the bulk copies; everyone waits on it.
+__device__ __forceinline__ void stage_scene(const RenderParams &P, unsigned char *smem_raw, const float4 *&s_nodes,
+                                            const float4 *&s_geom) {
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+  float4 *nodes_dst = reinterpret_cast<float4 *>(smem_raw + 128);
+  float4 *geom_dst = nodes_dst + 4 * (size_t)P.smem_nodes;
+  const uint32_t node_bytes = (uint32_t)P.smem_nodes * 64u, geom_bytes = (uint32_t)P.smem_spheres * 16u;
+  if (threadIdx.x == 0) mbar_init(bar, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, node_bytes + geom_bytes);
+    constexpr uint32_t kChunk = 32768;
+    for (uint32_t off = 0; off < node_bytes; off += kChunk)
+      tma_bulk_g2s(reinterpret_cast<unsigned char *>(nodes_dst) + off, reinterpret_cast<const unsigned char *>(P.nodes) + off,
+                   min(kChunk, node_bytes - off), bar);
+    for (uint32_t off = 0; off < geom_bytes; off += kChunk)
+      tma_bulk_g2s(reinterpret_cast<unsigned char *>(geom_dst) + off, reinterpret_cast<const unsigned char *>(P.geom) + off,
+                   min(kChunk, geom_bytes - off), bar);
+  }
+  mbar_wait(bar, 0);
+  s_nodes = nodes_dst;
+  s_geom = geom_dst;
+}
+
+// ====================================================================================== K1: persistent + refill
+// Persistent CTAs (grid = SMs x resident CTAs).  Every lane owns one pixel at a time and runs its
+// samples and bounces; whenever enough lanes of a warp are idle the warp claims new pixels from a
+// global cursor with one warp-aggregated atomicAdd (ballot + popc), so irreg's empty-sky rows and
+// rgbbox's 50-bounce tails never leave a warp mostly empty.  Samples of one pixel are summed in
+// sample order in a register, which is what the spp extension requires.
+template <bool kAllNodes, bool kSpheres>
+__global__ void __launch_bounds__(256, 2) render_persistent_kernel(const __grid_constant__ RenderParams P,
+                                                                    const int refill_min) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const float4 *s_nodes, *s_geom;
+  stage_scene(P, smem_raw, s_nodes, s_geom);
+  const StagedScene<kAllNodes, kSpheres> sc{P.nodes, P.geom, s_nodes, s_geom, P.smem_nodes};
+
+  const int lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const long long total64 = P.local_tiles * kTilePixels;
+  const int total = (int)total64;
+  WorkCounters wc;
+
+  int item = -1, pi = 0, pj = 0, s = 0, depth = 0;
+  Ray r;
+  V3 light, sum;
+  bool exhausted = false;  // warp-uniform: the cursor has run past the end
+  r.o = r.d = light = sum = v3(0.0f, 0.0f, 0.0f);
+
+  for (;;) {
+    unsigned idle = __ballot_sync(kFullMask, item < 0);
+    if (idle && !exhausted && (__popc(idle) >= refill_min || idle == kFullMask)) {
+      const int cnt = __popc(idle);
+      const int leader = __ffs(idle) - 1;
+      int base = 0;
+      if (lane == leader) base = atomicAdd(P.work_cursor, cnt);
+      base = __shfl_sync(kFullMask, base, leader);
+      if (item < 0) {
+        const int k = base + __popc(idle & lt_mask);
+        if (k < total) {
+          if (item_pixel(P, k, pi, pj)) {
+            item = k;
+            s = 0;
+            depth = 0;
+            r = primary_ray(P, pi, pj, 0);
+            light = v3(1.0f, 1.0f, 1.0f);
+          } else if (P.tile_major) {
+            P.out_pix[k] = 0;
+          }
+        }
+      }
+      exhausted = base + cnt >= total;
+      idle = __ballot_sync(kFullMask, item < 0);
+    }
+    if (idle == kFullMask) {
+      if (exhausted) break;
+      continue;  // every claimed item was a padding pixel: claim again
+    }
+    if (item >= 0) {
+      V3 colour;
+      if (!advance_path<false>(sc, P, r, light, depth, colour, wc)) {
+        sum = (s == 0) ? colour : vadd(sum, colour);
+        s++;
+        if (s < P.spp) {
+          depth = 0;
+          r = primary_ray(P, pi, pj, s);
+          light = v3(1.0f, 1.0f, 1.0f);
+        } else {
+          write_pixel(P, item, pi, pj, sum);
+          item = -1;
+        }
+      }
+    }
+  }
+}
+
+// ====================================================================================== de-tiling (multi-GPU)
+// gathered: [world][tiles_padded][32] as an NCCL gather of every rank's compact buffer lays it out.
+__global__ void detile_kernel(const int32_t *__restrict__ gathered, int32_t *__restrict__ out, int H, int W, int world,
+                              long long tiles_padded, int tiles_x) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)H * W) return;
+  const int j = (int)(idx / W), i = (int)(idx - (long long)j * W);
+  const long long t = (long long)(j / kTileH) * tiles_x + (i / kTileW);
+  const int sub = (j % kTileH) * kTileW + (i % kTileW);
+  const long long rank = t % world, lt = t / world;
+  out[idx] = gathered[(rank * tiles_padded + lt) * kTilePixels + sub];
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------- host launchers
+size_t staging_bytes(const RenderParams &p) { return 128 + (size_t)p.smem_nodes * 64 + (size_t)p.smem_spheres * 16; }
+
+cudaError_t configure_kernels(int max_dynamic_smem) {
+  cudaError_t e;
+#define RAYB200_SET(k)                                                                          \
+  e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dynamic_smem);   \
+  if (e != cudaSuccess) return e;
+  RAYB200_SET((render_persistent_kernel<true, true>));
+  RAYB200_SET((render_persistent_kernel<true, false>));
+  RAYB200_SET((render_persistent_kernel<false, true>));
+  RAYB200_SET((render_persistent_kernel<false, false>));
+#undef RAYB200_SET
+  return cudaSuccess;
+}
+
+void launch_render(const RenderParams &p, const LaunchConfig &lc, const WavefrontBuffers *wf, cudaStream_t stream,
+                   int64_t *launches) {
+  (void)wf;
+  const long long items = p.local_tiles * kTilePixels;
+  if (items <= 0) return;
+  if (lc.kernel == 1) {  // RAY_B200_KERNEL_MEGA
+    const int threads = 128;
+    const unsigned blocks = (unsigned)((items + threads - 1) / threads);
+    render_mega_kernel<false><<<blocks, threads, 0, stream>>>(p);
+    (*launches)++;
+    return;
+  }
+  // RAY_B200_KERNEL_PERSISTENT
+  const int threads = 256;
+  long long want = (long long)lc.sm_count * lc.blocks_per_sm;
+  const long long max_useful = (items + threads - 1) / threads;
+  if (want > max_useful) want = max_useful;
+  const size_t smem = staging_bytes(p);
+  const bool all_nodes = p.smem_nodes == p.n_inner, sph = p.smem_spheres == p.n_leaves && p.smem_spheres > 0;
+  const int refill = lc.refill_min < 1 ? 1 : (lc.refill_min > 32 ? 32 : lc.refill_min);
+  if (all_nodes && sph) render_persistent_kernel<true, true><<<(unsigned)want, threads, smem, stream>>>(p, refill);
+  else if (all_nodes) render_persistent_kernel<true, false><<<(unsigned)want, threads, smem, stream>>>(p, refill);
+  else if (sph) render_persistent_kernel<false, true><<<(unsigned)want, threads, smem, stream>>>(p, refill);
+  else render_persistent_kernel<false, false><<<(unsigned)want, threads, smem, stream>>>(p, refill);
+  (*launches)++;
+}
+
+void launch_count_work(const RenderParams &p, cudaStream_t stream, int64_t *launches) {
+  const long long items = p.local_tiles * kTilePixels;
+  if (items <= 0) return;
+  const int threads = 128;
+  const unsigned blocks = (unsigned)((items + threads - 1) / threads);
+  render_mega_kernel<true><<<blocks, threads, 0, stream>>>(p);
+  (*launches)++;
+}
+
+void launch_detile(const int32_t *gathered, int32_t *out, int64_t H, int64_t W, int32_t world, int64_t tiles_padded,
+                   cudaStream_t stream, int64_t *launches) {
+  const long long n = (long long)H * W;
+  if (n <= 0) return;
+  const int threads = 256;
+  const int tiles_x = (int)((W + kTileW - 1) / kTileW);
+  detile_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, stream>>>(gathered, out, (int)H, (int)W, world,
+                                                                                 tiles_padded, tiles_x);
+  (*launches)++;
+}
+
+}  // namespace rayb200

@@ -1,0 +1,66 @@
+// Kernel parameter block shared by the host API (api.cu) and the kernels (render_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace rayb200 {
+
+constexpr int kTileW = 8;       // a warp renders an 8x4-pixel tile (coherent primary rays, 128-B stores)
+constexpr int kTileH = 4;
+constexpr int kTilePixels = 32;
+constexpr int kMaxDepth = 50;   // ray.fut:154 `ray_colour objs ray 50`
+constexpr int kStackSize = 64;  // a radix tree over (32-bit key, 32-bit index) is at most 64 deep
+
+struct RenderParams {
+  // prepared scene (device layout of scene_host.h PackedBvh)
+  const float4 *nodes;
+  const float4 *geom;
+  const float4 *colour;
+  int32_t n_inner, n_leaves;
+  int32_t smem_nodes;    // first smem_nodes BFS nodes are staged in shared memory (persistent/wavefront kernels)
+  int32_t smem_spheres;  // first smem_spheres sphere records staged (0 or n_leaves)
+  float root_box[6];
+  float cam[12];         // origin, llc, horizontal, vertical (ray.fut:88-91)
+  // frame
+  int32_t W, H, spp;
+  float inv_spp;
+  const float *offsets;  // 2*spp sample offsets (device)
+  int32_t *out_pix;      // row-major [H][W] (tile_major == 0) or compact [local_tiles][32] (tile_major == 1)
+  float *out_rgb;        // optional [H][W][3]
+  int32_t tile_major;
+  // sharding: this rank renders tiles t = lt * world + rank
+  int32_t rank, world, tiles_x, tiles_y;
+  int64_t n_tiles, local_tiles;
+  // persistent-threads work cursor and optional work counters
+  int32_t *work_cursor;
+  unsigned long long *counters;  // [4] segments, node_steps, box_tests, leaf_tests (counting kernels only)
+};
+
+// wavefront ray record (SoA in HBM): see render_kernels.cu
+struct WavefrontBuffers {
+  float4 *ray_o[2];   // {o.xyz, bits(path id)}
+  float4 *ray_d[2];   // {d.xyz, unused}
+  float4 *light[2];   // {light.rgb, bits(depth)}
+  int32_t *queue_len; // [kMaxDepth + 2]
+  float4 *accum;      // per local pixel {sum.rgb, unused}
+  int64_t capacity;
+};
+
+struct LaunchConfig {
+  int kernel;          // ray_b200_kernel
+  int block_threads;   // persistent/wavefront CTA size
+  int blocks_per_sm;
+  int sm_count;
+  int smem_budget;     // bytes of dynamic shared memory per CTA for BVH staging
+  int refill_min;      // persistent kernel: refill when at least this many lanes are idle
+};
+
+void launch_render(const RenderParams &p, const LaunchConfig &lc, const WavefrontBuffers *wf, cudaStream_t stream,
+                   int64_t *launches);
+void launch_count_work(const RenderParams &p, cudaStream_t stream, int64_t *launches);
+void launch_detile(const int32_t *gathered, int32_t *out, int64_t H, int64_t W, int32_t world, int64_t tiles_padded,
+                   cudaStream_t stream, int64_t *launches);
+size_t staging_bytes(const RenderParams &p);
+cudaError_t configure_kernels(int max_dynamic_smem);
+
+}  // namespace rayb200

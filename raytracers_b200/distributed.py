@@ -1,0 +1,108 @@
+"""Multi-GPU host logic: one process per GPU (torchrun), image tiles sharded round-robin, one NCCL
+gather of the final framebuffer.
+
+The render path shards by pixels with no data-path exchange (pixels are independent, ray.fut:166-169):
+the prepared scene is replicated (<= 66 MB even for 1 M spheres), 8x4-pixel tile t belongs to rank
+t % world (contiguous bands would leave irreg's sky ranks idle), every rank renders its tiles into a
+compact tile-major buffer with the single-GPU kernels, and ONE collective — a gather of int32 tiles to
+rank 0 over NVLink — assembles the frame, which a de-tiling kernel turns back into [h][w].
+
+torch is used here only for device buffers and torch.distributed (plumbing).
+"""
+import numpy as np
+
+TILE_W, TILE_H, TILE_PIXELS = 8, 4, 32
+
+
+def tile_layout(h, w, world):
+    tiles_x = (w + TILE_W - 1) // TILE_W
+    tiles_y = (h + TILE_H - 1) // TILE_H
+    n_tiles = tiles_x * tiles_y
+    padded = (n_tiles + world - 1) // world
+    return tiles_x, tiles_y, n_tiles, padded
+
+
+def rank_tile_count(h, w, rank, world):
+    _, _, n_tiles, _ = tile_layout(h, w, world)
+    return n_tiles // world + (1 if (n_tiles % world) > rank else 0)
+
+
+def extract_rank_tiles(img, rank, world):
+    """CPU statement of what ray_b200_render_shard_into produces for `rank`: int32[padded][32]
+    (pixels outside the image and padding tiles are 0).  Used by tests and as documentation."""
+    h, w = img.shape
+    tiles_x, _, n_tiles, padded = tile_layout(h, w, world)
+    out = np.zeros((padded, TILE_PIXELS), np.int32)
+    for lt in range(padded):
+        t = lt * world + rank
+        if t >= n_tiles:
+            break
+        ty, tx = divmod(t, tiles_x)
+        blk = img[ty * TILE_H:(ty + 1) * TILE_H, tx * TILE_W:(tx + 1) * TILE_W]
+        full = np.zeros((TILE_H, TILE_W), np.int32)
+        full[:blk.shape[0], :blk.shape[1]] = blk
+        out[lt] = full.reshape(-1)
+    return out
+
+
+def detile_reference(gathered, h, w, world):
+    """CPU statement of ray_b200_detile: gathered int32[world][padded][32] -> int32[h][w]."""
+    tiles_x, _, _, padded = tile_layout(h, w, world)
+    g = np.asarray(gathered).reshape(world, padded, TILE_PIXELS)
+    jj, ii = np.meshgrid(np.arange(h), np.arange(w), indexing="ij")
+    t = (jj // TILE_H) * tiles_x + (ii // TILE_W)
+    sub = (jj % TILE_H) * TILE_W + (ii % TILE_W)
+    return g[t % world, t // world, sub].astype(np.int32)
+
+
+def gather_tiles(local_tiles, dst=0, group=None):
+    """The one collective of the path: gathers every rank's compact tile buffer on `dst`.
+    Returns a [world][padded][32] tensor on dst, None elsewhere."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if world == 1:
+        return local_tiles.reshape(1, *local_tiles.shape)
+    if rank == dst:
+        out = torch.empty((world,) + tuple(local_tiles.shape), dtype=local_tiles.dtype, device=local_tiles.device)
+        dist.gather(local_tiles, list(out.unbind(0)), dst=dst, group=group)
+        return out
+    dist.gather(local_tiles, None, dst=dst, group=group)
+    return None
+
+
+class ShardedRenderer:
+    """Per-rank driver: render this rank's tiles on its GPU, gather on rank 0, de-tile there."""
+
+    def __init__(self, ctx, rank, world):
+        import torch
+
+        self.ctx, self.rank, self.world = ctx, rank, world
+        self.torch = torch
+        ctx.set_shard(rank, world)
+        self._tiles = None
+        self._frame = None
+        self._key = None
+
+    def _buffers(self, h, w):
+        torch = self.torch
+        if self._key != (h, w):
+            _, _, _, padded = tile_layout(h, w, self.world)
+            dev = torch.device("cuda", self.ctx.device)
+            self._tiles = torch.empty((padded, TILE_PIXELS), dtype=torch.int32, device=dev)
+            self._frame = torch.empty((h, w), dtype=torch.int32, device=dev) if self.rank == 0 else None
+            self._key = (h, w)
+        return self._tiles, self._frame
+
+    def render(self, h, w, prepared, spp=1):
+        """Returns the full frame (device int32[h][w]) on rank 0, None on the other ranks.  Asynchronous
+        on torch's current stream (the context must have been pointed at it with ctx.set_stream)."""
+        tiles, frame = self._buffers(h, w)
+        self.ctx.render_shard_into(tiles.data_ptr(), h, w, prepared, spp)
+        gathered = gather_tiles(tiles, dst=0)
+        if self.rank != 0:
+            return None
+        self.ctx.detile(gathered.data_ptr(), frame.data_ptr(), h, w, self.world)
+        return frame
