@@ -25,7 +25,7 @@ struct futhark_context_config {
   int32_t spp = 1;
   int32_t kernel = RAY_B200_KERNEL_AUTO;
   int32_t rank = 0, world = 1;
-  int32_t block_threads = 256, blocks_per_sm = 2, smem_budget = 64 * 1024, refill_min = 8;
+  int32_t block_threads = 256, blocks_per_sm = 2, smem_budget = 64 * 1024, refill_min = 8, tail_from = 8;
   std::string cache_file;
 };
 
@@ -43,6 +43,7 @@ struct futhark_context {
   float *offsets = nullptr;                 // device sample-offset table
   int32_t offsets_spp = 0;
   int64_t launches = 0;
+  WavefrontBuffers wf;                      // ray queues of the wavefront kernel (grown on demand)
   bool profiling_paused = false;
   double total_render_ms = 0.0;
   int64_t renders = 0;
@@ -110,7 +111,7 @@ int parse_kernel(const char *v, int dflt) {
   return atoi(v);
 }
 
-const char *kTuningNames[] = {"kernel", "spp", "blocks_per_sm", "smem_budget", "refill_min", "rank", "world"};
+const char *kTuningNames[] = {"kernel", "spp", "blocks_per_sm", "smem_budget", "refill_min", "tail_from", "rank", "world"};
 constexpr int kNumTuning = sizeof(kTuningNames) / sizeof(kTuningNames[0]);
 
 bool bad_ctx(futhark_context *ctx) { return ctx == nullptr || !ctx->ok; }
@@ -170,8 +171,40 @@ int fill_params(futhark_context *ctx, const futhark_opaque_prepared_scene *p, in
 int resolve_kernel(const futhark_context *ctx) {
   int k = ctx->cfg.kernel;
   if (k == RAY_B200_KERNEL_AUTO) k = RAY_B200_KERNEL_PERSISTENT;
-  if (k == RAY_B200_KERNEL_WAVEFRONT) k = RAY_B200_KERNEL_PERSISTENT;  // TODO(wavefront): falls back until K2 lands
   return k;
+}
+
+void free_wavefront(futhark_context *ctx) {
+  WavefrontBuffers &b = ctx->wf;
+  for (int q = 0; q < 2; q++) {
+    if (b.ray_o[q]) cudaFree(b.ray_o[q]);
+    if (b.ray_d[q]) cudaFree(b.ray_d[q]);
+    if (b.light[q]) cudaFree(b.light[q]);
+  }
+  if (b.qlen) cudaFree(b.qlen);
+  if (b.accum) cudaFree(b.accum);
+  memset(&b, 0, sizeof b);
+}
+
+// Ray queues: 2 x 48 B per local pixel (+16 B accumulator), resident for the life of the context.
+int ensure_wavefront(futhark_context *ctx, int64_t items) {
+  WavefrontBuffers &b = ctx->wf;
+  b.tail_from = ctx->cfg.tail_from;
+  if (b.capacity >= items) return 0;
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  free_wavefront(ctx);
+  b.tail_from = ctx->cfg.tail_from;
+  const size_t bytes = (size_t)items * sizeof(float4);
+  for (int q = 0; q < 2; q++) {
+    CUDA_TRY(ctx, cudaMalloc(&b.ray_o[q], bytes));
+    CUDA_TRY(ctx, cudaMalloc(&b.ray_d[q], bytes));
+    CUDA_TRY(ctx, cudaMalloc(&b.light[q], bytes));
+  }
+  CUDA_TRY(ctx, cudaMalloc(&b.accum, bytes));
+  CUDA_TRY(ctx, cudaMalloc(&b.qlen, 2 * (kMaxDepth + 2) * sizeof(int32_t)));
+  b.cursor = b.qlen + (kMaxDepth + 2);
+  b.capacity = items;
+  return 0;
 }
 
 int do_render(futhark_context *ctx, const RenderParams &P) {
@@ -182,9 +215,11 @@ int do_render(futhark_context *ctx, const RenderParams &P) {
   lc.sm_count = ctx->sm_count;
   lc.smem_budget = ctx->cfg.smem_budget;
   lc.refill_min = ctx->cfg.refill_min;
+  lc.tail_from = ctx->cfg.tail_from;
+  if (lc.kernel == RAY_B200_KERNEL_WAVEFRONT && ensure_wavefront(ctx, P.local_tiles * kTilePixels)) return 1;
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev_start, ctx->stream));
-  if (lc.kernel != RAY_B200_KERNEL_MEGA) CUDA_TRY(ctx, cudaMemsetAsync(ctx->work_cursor, 0, sizeof(int32_t), ctx->stream));
-  launch_render(P, lc, nullptr, ctx->stream, &ctx->launches);
+  if (lc.kernel == RAY_B200_KERNEL_PERSISTENT) CUDA_TRY(ctx, cudaMemsetAsync(ctx->work_cursor, 0, sizeof(int32_t), ctx->stream));
+  launch_render(P, lc, &ctx->wf, ctx->stream, &ctx->launches);
   CUDA_TRY(ctx, cudaGetLastError());
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev_stop, ctx->stream));
   ctx->have_timing = true;
@@ -256,6 +291,7 @@ int futhark_context_config_set_tuning_param(struct futhark_context_config *cfg, 
   else if (!strcmp(name, "blocks_per_sm")) cfg->blocks_per_sm = (int32_t)v;
   else if (!strcmp(name, "smem_budget")) cfg->smem_budget = (int32_t)v;
   else if (!strcmp(name, "refill_min")) cfg->refill_min = (int32_t)v;
+  else if (!strcmp(name, "tail_from")) cfg->tail_from = (int32_t)v;
   else if (!strcmp(name, "rank")) cfg->rank = (int32_t)v;
   else if (!strcmp(name, "world")) cfg->world = (int32_t)v;
   else return 1;
@@ -275,6 +311,8 @@ struct futhark_context *futhark_context_new(struct futhark_context_config *cfg) 
   ctx->cfg.blocks_per_sm = env_int("RAY_BLOCKS_PER_SM", ctx->cfg.blocks_per_sm);
   ctx->cfg.smem_budget = env_int("RAY_SMEM_BUDGET", ctx->cfg.smem_budget);
   ctx->cfg.refill_min = env_int("RAY_REFILL_MIN", ctx->cfg.refill_min);
+  ctx->cfg.tail_from = env_int("RAY_TAIL_FROM", ctx->cfg.tail_from);
+  memset(&ctx->wf, 0, sizeof ctx->wf);
 
   auto fail = [&](const char *what, cudaError_t e) {
     set_error(ctx, "futhark_context_new: %s: %s (this library has no CPU fallback)", what, cudaGetErrorString(e));
@@ -317,6 +355,7 @@ void futhark_context_free(struct futhark_context *ctx) {
     cudaSetDevice(ctx->cfg.device);
     cudaStreamSynchronize(ctx->stream);
   }
+  if (ctx->ok) free_wavefront(ctx);
   if (ctx->offsets) cudaFree(ctx->offsets);
   if (ctx->work_cursor) cudaFree(ctx->work_cursor);
   if (ctx->counters) cudaFree(ctx->counters);

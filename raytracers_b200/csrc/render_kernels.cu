@@ -352,6 +352,96 @@ __global__ void __launch_bounds__(256, 2) render_persistent_kernel(const __grid_
   }
 }
 
+// ====================================================================================== K2: wavefront
+// The north-star design: ONE persistent-threads kernel launch per bounce.  Warps claim batches of 32
+// rays from the bounce's global queue with an atomic cursor, trace one segment (same traversal as K1,
+// BVH staged by TMA), shade, and append the survivors to the next bounce's queue with warp-vote
+// compaction (ballot + popc + one atomicAdd per warp), so every bounce runs on densely packed warps
+// whatever the image-space distribution of live paths is.  Bounce 0 generates its rays instead of
+// reading them; terminated paths write their pixel (spp == 1) or add into an in-order accumulator.
+// From bounce `tail_from` on, the handful of surviving rays are run to completion inside one launch
+// instead of paying ~40 more near-empty launches.
+template <bool kAllNodes, bool kSpheres>
+__global__ void __launch_bounds__(256, 2) wavefront_bounce_kernel(const __grid_constant__ RenderParams P,
+                                                                   const __grid_constant__ WavefrontBuffers B,
+                                                                   const int bounce, const int sample,
+                                                                   const int run_to_end) {
+  const long long total64 = P.local_tiles * kTilePixels;
+  const int n_in = bounce == 0 ? (int)total64 : B.qlen[bounce];
+  if ((long long)blockIdx.x * 32 >= n_in) return;  // nothing for this CTA: skip the staging too
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const float4 *s_nodes, *s_geom;
+  stage_scene(P, smem_raw, s_nodes, s_geom);
+  const StagedScene<kAllNodes, kSpheres> sc{P.nodes, P.geom, s_nodes, s_geom, P.smem_nodes};
+  const int lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const int qi = bounce & 1, qo = qi ^ 1;
+  const bool last_sample = sample == P.spp - 1;
+  WorkCounters wc;
+  for (;;) {
+    int base = 0;
+    if (lane == 0) base = atomicAdd(B.cursor + bounce, 32);
+    base = __shfl_sync(kFullMask, base, 0);
+    if (base >= n_in) break;
+    const int idx = base + lane;
+    bool active = idx < n_in;
+    Ray r;
+    V3 light = v3(1.0f, 1.0f, 1.0f);
+    int pid = idx, depth = bounce;
+    r.o = r.d = v3(0.0f, 0.0f, 0.0f);
+    if (active) {
+      if (bounce == 0) {
+        int i, j;
+        active = item_pixel(P, idx, i, j);
+        if (active) r = primary_ray(P, i, j, sample);
+        else if (P.tile_major && last_sample) P.out_pix[idx] = 0;
+      } else {
+        const float4 a = B.ray_o[qi][idx], d = B.ray_d[qi][idx], l = B.light[qi][idx];
+        r.o = v3(a.x, a.y, a.z);
+        r.d = v3(d.x, d.y, d.z);
+        light = v3(l.x, l.y, l.z);
+        pid = __float_as_int(a.w);
+      }
+    }
+    bool cont = false;
+    if (active) {
+      V3 colour;
+      cont = advance_path<false>(sc, P, r, light, depth, colour, wc);
+      if (run_to_end)
+        while (cont) cont = advance_path<false>(sc, P, r, light, depth, colour, wc);
+      if (!cont) {  // path ended: this sample's colour goes to its pixel, in sample order
+        int i, j;
+        item_pixel(P, pid, i, j);
+        if (P.spp == 1) {
+          write_pixel(P, pid, i, j, colour);
+        } else {
+          V3 sum = colour;
+          if (sample > 0) {
+            const float4 acc = B.accum[pid];
+            sum = vadd(v3(acc.x, acc.y, acc.z), colour);
+          }
+          if (last_sample) write_pixel(P, pid, i, j, sum);
+          else B.accum[pid] = make_float4(sum.x, sum.y, sum.z, 0.0f);
+        }
+      }
+    }
+    // warp-vote compaction of the survivors into the next bounce's queue
+    const unsigned alive = __ballot_sync(kFullMask, cont);
+    if (alive) {
+      const int leader = __ffs(alive) - 1;
+      int obase = 0;
+      if (lane == leader) obase = atomicAdd(B.qlen + bounce + 1, __popc(alive));
+      obase = __shfl_sync(kFullMask, obase, leader);
+      if (cont) {
+        const int o = obase + __popc(alive & lt_mask);
+        B.ray_o[qo][o] = make_float4(r.o.x, r.o.y, r.o.z, __int_as_float(pid));
+        B.ray_d[qo][o] = make_float4(r.d.x, r.d.y, r.d.z, 0.0f);
+        B.light[qo][o] = make_float4(light.x, light.y, light.z, 0.0f);
+      }
+    }
+  }
+}
+
 // ====================================================================================== de-tiling (multi-GPU)
 // gathered: [world][tiles_padded][32] as an NCCL gather of every rank's compact buffer lays it out.
 __global__ void detile_kernel(const int32_t *__restrict__ gathered, int32_t *__restrict__ out, int H, int W, int world,
@@ -379,13 +469,16 @@ cudaError_t configure_kernels(int max_dynamic_smem) {
   RAYB200_SET((render_persistent_kernel<true, false>));
   RAYB200_SET((render_persistent_kernel<false, true>));
   RAYB200_SET((render_persistent_kernel<false, false>));
+  RAYB200_SET((wavefront_bounce_kernel<true, true>));
+  RAYB200_SET((wavefront_bounce_kernel<true, false>));
+  RAYB200_SET((wavefront_bounce_kernel<false, true>));
+  RAYB200_SET((wavefront_bounce_kernel<false, false>));
 #undef RAYB200_SET
   return cudaSuccess;
 }
 
 void launch_render(const RenderParams &p, const LaunchConfig &lc, const WavefrontBuffers *wf, cudaStream_t stream,
                    int64_t *launches) {
-  (void)wf;
   const long long items = p.local_tiles * kTilePixels;
   if (items <= 0) return;
   if (lc.kernel == 1) {  // RAY_B200_KERNEL_MEGA
@@ -395,13 +488,30 @@ void launch_render(const RenderParams &p, const LaunchConfig &lc, const Wavefron
     (*launches)++;
     return;
   }
-  // RAY_B200_KERNEL_PERSISTENT
   const int threads = 256;
-  long long want = (long long)lc.sm_count * lc.blocks_per_sm;
-  const long long max_useful = (items + threads - 1) / threads;
-  if (want > max_useful) want = max_useful;
   const size_t smem = staging_bytes(p);
   const bool all_nodes = p.smem_nodes == p.n_inner, sph = p.smem_spheres == p.n_leaves && p.smem_spheres > 0;
+  long long want = (long long)lc.sm_count * lc.blocks_per_sm;
+  if (lc.kernel == 3) {  // RAY_B200_KERNEL_WAVEFRONT: per sample pass, one launch per bounce up to the tail bounce
+    const long long max_useful = (items + 31) / 32;
+    if (want > max_useful) want = max_useful;
+    const int tail = wf->tail_from < 0 ? 0 : (wf->tail_from > kMaxDepth - 1 ? kMaxDepth - 1 : wf->tail_from);
+    for (int s = 0; s < p.spp; s++) {
+      cudaMemsetAsync(wf->qlen, 0, 2 * (kMaxDepth + 2) * sizeof(int32_t), stream);  // qlen and cursor are contiguous
+      for (int b = 0; b <= tail; b++) {
+        const int rte = b == tail;
+        if (all_nodes && sph) wavefront_bounce_kernel<true, true><<<(unsigned)want, threads, smem, stream>>>(p, *wf, b, s, rte);
+        else if (all_nodes) wavefront_bounce_kernel<true, false><<<(unsigned)want, threads, smem, stream>>>(p, *wf, b, s, rte);
+        else if (sph) wavefront_bounce_kernel<false, true><<<(unsigned)want, threads, smem, stream>>>(p, *wf, b, s, rte);
+        else wavefront_bounce_kernel<false, false><<<(unsigned)want, threads, smem, stream>>>(p, *wf, b, s, rte);
+        (*launches)++;
+      }
+    }
+    return;
+  }
+  // RAY_B200_KERNEL_PERSISTENT
+  const long long max_useful = (items + threads - 1) / threads;
+  if (want > max_useful) want = max_useful;
   const int refill = lc.refill_min < 1 ? 1 : (lc.refill_min > 32 ? 32 : lc.refill_min);
   if (all_nodes && sph) render_persistent_kernel<true, true><<<(unsigned)want, threads, smem, stream>>>(p, refill);
   else if (all_nodes) render_persistent_kernel<true, false><<<(unsigned)want, threads, smem, stream>>>(p, refill);

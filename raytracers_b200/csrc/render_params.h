@@ -36,14 +36,16 @@ struct RenderParams {
   unsigned long long *counters;  // [4] segments, node_steps, box_tests, leaf_tests (counting kernels only)
 };
 
-// wavefront ray record (SoA in HBM): see render_kernels.cu
+// Wavefront ray queues (SoA in HBM, 48 B per live ray): two ping-pong queues indexed by bounce parity.
 struct WavefrontBuffers {
-  float4 *ray_o[2];   // {o.xyz, bits(path id)}
-  float4 *ray_d[2];   // {d.xyz, unused}
-  float4 *light[2];   // {light.rgb, bits(depth)}
-  int32_t *queue_len; // [kMaxDepth + 2]
-  float4 *accum;      // per local pixel {sum.rgb, unused}
-  int64_t capacity;
+  float4 *ray_o[2];   // {origin.xyz, bits(path id = local item index)}
+  float4 *ray_d[2];   // {dir.xyz, 0}
+  float4 *light[2];   // {light.rgb, 0}
+  int32_t *qlen;      // [kMaxDepth + 2] rays queued for bounce b (written by bounce b-1's compaction)
+  int32_t *cursor;    // [kMaxDepth + 2] persistent-threads work cursor of bounce b
+  float4 *accum;      // per local item {sum.rgb, 0}: in-order sample accumulation when spp > 1
+  int64_t capacity;   // items the queues can hold
+  int32_t tail_from;  // bounce whose kernel runs the (few) surviving rays to completion
 };
 
 struct LaunchConfig {
@@ -53,6 +55,7 @@ struct LaunchConfig {
   int sm_count;
   int smem_budget;     // bytes of dynamic shared memory per CTA for BVH staging
   int refill_min;      // persistent kernel: refill when at least this many lanes are idle
+  int tail_from;       // wavefront: see WavefrontBuffers
 };
 
 void launch_render(const RenderParams &p, const LaunchConfig &lc, const WavefrontBuffers *wf, cudaStream_t stream,
