@@ -178,7 +178,8 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     ctx = R.Context(device=local_rank, kernel=args.kernel)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()          # one stream for the library's kernels, NCCL and the timing events
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     prepared = {name: ctx.prepare_scene(H, W, ctx.scene(name)) for name in SCENES}
     ctx.sync()

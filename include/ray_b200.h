@@ -29,12 +29,14 @@ enum ray_b200_kernel {
   RAY_B200_KERNEL_AUTO = 0,       /* pick the fastest measured variant */
   RAY_B200_KERNEL_MEGA = 1,       /* one thread per pixel, whole ray_colour loop (parity anchor) */
   RAY_B200_KERNEL_PERSISTENT = 2, /* persistent CTAs, TMA-staged BVH, per-lane dynamic path refill */
-  RAY_B200_KERNEL_WAVEFRONT = 3   /* generate -> per-bounce persistent kernel + ray queues -> pack */
+  RAY_B200_KERNEL_WAVEFRONT = 3,  /* per-bounce persistent kernel + global ray queues + warp-vote compaction */
+  RAY_B200_KERNEL_WARPQUEUE = 4   /* persistent; lanes bound to (ray,node) items on warp-private smem queues */
 };
 
 /* ---- context extensions ---------------------------------------------------------------------- */
 /* Launch all work of this context on `cuda_stream` (a cudaStream_t / CUstream, e.g.
- * torch.cuda.current_stream().cuda_stream).  NULL restores the context's own stream. */
+ * torch.cuda.Stream.cuda_stream).  NULL restores the context's own stream; pass cudaStreamLegacy
+ * ((cudaStream_t)0x1) for the legacy default stream (whose raw handle is 0). */
 int ray_b200_context_set_stream(struct futhark_context *ctx, void *cuda_stream);
 /* Samples per pixel used by futhark_entry_render (default 1 = the reference). */
 int ray_b200_context_set_spp(struct futhark_context *ctx, int32_t spp);

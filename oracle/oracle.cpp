@@ -498,15 +498,19 @@ int oracle_render(void *pv, int64_t h, int64_t w, int32_t spp, int32_t *out_pix,
   int nthreads = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
   if (nthreads < 1) nthreads = 1;
   const int64_t nrows = (h - row_start + row_step - 1) / row_step;
-  if (nthreads > nrows) nthreads = (int)std::max<int64_t>(nrows, 1);
-  std::atomic<int64_t> next_row{0};  // dynamic row scheduling (irreg is load-imbalanced by rows)
+  const int64_t span = 64;                       // work unit: 64 consecutive pixels of one row
+  const int64_t spans_per_row = (w + span - 1) / span;
+  const int64_t nunits = nrows * spans_per_row;
+  if (nthreads > nunits) nthreads = (int)std::max<int64_t>(nunits, 1);
+  std::atomic<int64_t> next_unit{0};  // dynamic scheduling (irreg is load-imbalanced by rows)
   auto worker = [&]() {
     Counters local;
     for (;;) {
-      int64_t r = next_row.fetch_add(1);
-      if (r >= nrows) break;
-      int64_t j = row_start + r * row_step;                      // ray.fut:166-169 tabulate_2d height width
-      for (int64_t i = 0; i < w; i++) {
+      int64_t unit = next_unit.fetch_add(1);
+      if (unit >= nunits) break;
+      const int64_t r = unit / spans_per_row, i0 = (unit % spans_per_row) * span;
+      const int64_t j = row_start + r * row_step;                // ray.fut:166-169 tabulate_2d height width
+      for (int64_t i = i0; i < std::min(w, i0 + span); i++) {
         V3 sum = vec(0, 0, 0);
         for (int32_t s = 0; s < spp; s++) {
           // ray.fut:150-154 with pixel j i = trace_ray ... (height-j) i (ray.fut:167-168)

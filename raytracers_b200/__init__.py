@@ -24,7 +24,7 @@ __all__ = ["Context", "RayError", "lib_path", "load_library", "KERNELS", "declar
            "host_camera", "host_lbvh", "host_sample_offsets"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-KERNELS = {"auto": 0, "mega": 1, "persistent": 2, "wavefront": 3}
+KERNELS = {"auto": 0, "mega": 1, "persistent": 2, "wavefront": 3, "warpqueue": 4}
 
 
 class RayError(RuntimeError):
@@ -410,7 +410,14 @@ class Context:
         return PreparedScene(self, h)
 
     def set_stream(self, cuda_stream):
-        self._check(self.lib.ray_b200_context_set_stream(self.handle, C.c_void_p(int(cuda_stream) if cuda_stream else None)))
+        """cuda_stream: a cudaStream_t handle (torch.cuda.Stream.cuda_stream).  torch's default stream has
+        handle 0, which the C API reads as "restore the context's own stream"; it is passed as
+        cudaStreamLegacy (0x1) instead so the work really lands on the default stream.  None restores."""
+        if cuda_stream is None:
+            h = None
+        else:
+            h = int(cuda_stream) or 1
+        self._check(self.lib.ray_b200_context_set_stream(self.handle, C.c_void_p(h)))
 
     def set_spp(self, spp):
         self._check(self.lib.ray_b200_context_set_spp(self.handle, int(spp)))

@@ -25,7 +25,8 @@ struct futhark_context_config {
   int32_t spp = 1;
   int32_t kernel = RAY_B200_KERNEL_AUTO;
   int32_t rank = 0, world = 1;
-  int32_t block_threads = 256, blocks_per_sm = 2, smem_budget = 64 * 1024, refill_min = 8, tail_from = 8;
+  int32_t block_threads = 256, blocks_per_sm = 4, smem_budget = 48 * 1024, refill_min = 8, tail_from = 8;
+  int32_t wq_warps = 16, wq_k = 2;
   std::string cache_file;
 };
 
@@ -108,10 +109,11 @@ int parse_kernel(const char *v, int dflt) {
   if (!strcmp(v, "mega")) return RAY_B200_KERNEL_MEGA;
   if (!strcmp(v, "persistent")) return RAY_B200_KERNEL_PERSISTENT;
   if (!strcmp(v, "wavefront")) return RAY_B200_KERNEL_WAVEFRONT;
+  if (!strcmp(v, "warpqueue")) return RAY_B200_KERNEL_WARPQUEUE;
   return atoi(v);
 }
 
-const char *kTuningNames[] = {"kernel", "spp", "blocks_per_sm", "smem_budget", "refill_min", "tail_from", "rank", "world"};
+const char *kTuningNames[] = {"kernel", "spp", "blocks_per_sm", "smem_budget", "refill_min", "tail_from", "wq_warps", "wq_k", "rank", "world"};
 constexpr int kNumTuning = sizeof(kTuningNames) / sizeof(kTuningNames[0]);
 
 bool bad_ctx(futhark_context *ctx) { return ctx == nullptr || !ctx->ok; }
@@ -134,6 +136,8 @@ int64_t tiles_of_rank(int64_t h, int64_t w, int32_t rank, int32_t world) {
   return t / world + ((t % world) > rank ? 1 : 0);
 }
 
+int resolve_kernel(const futhark_context *ctx);
+
 // Fills the kernel parameter block for one frame.
 int fill_params(futhark_context *ctx, const futhark_opaque_prepared_scene *p, int64_t h, int64_t w, int32_t spp,
                 int32_t rank, int32_t world, int32_t *out_pix, float *out_rgb, bool tile_major, RenderParams &P) {
@@ -146,6 +150,7 @@ int fill_params(futhark_context *ctx, const futhark_opaque_prepared_scene *p, in
   memset(&P, 0, sizeof P);
   P.nodes = p->d_nodes; P.geom = p->d_geom; P.colour = p->d_colour;
   P.n_inner = (int32_t)(p->n - 1); P.n_leaves = (int32_t)p->n;
+  P.max_depth = p->max_depth;
   memcpy(P.root_box, p->root_box, sizeof P.root_box);
   // The camera depends on the aspect ratio w/h given to prepare_scene (ray.fut:243-244); render's own
   // h, w only set the pixel grid (ray.fut:246-247) — exactly as in the reference.
@@ -159,8 +164,15 @@ int fill_params(futhark_context *ctx, const futhark_opaque_prepared_scene *p, in
   P.local_tiles = tiles_of_rank(h, w, rank, world);
   P.work_cursor = ctx->work_cursor;
   P.counters = ctx->counters;
-  // shared-memory staging plan: BFS prefix of the node array, then the sphere records if they all fit
-  const int64_t budget = std::min<int64_t>(ctx->cfg.smem_budget, ctx->max_smem_optin - 1024) - 128;
+  // shared-memory staging plan: BFS prefix of the node array, then the sphere records if they all fit.
+  // The warp-queue kernel runs one CTA per SM and gives the staging area whatever its queues leave.
+  int64_t budget = std::min<int64_t>(ctx->cfg.smem_budget, ctx->max_smem_optin - 1024) - 128;
+  if (resolve_kernel(ctx) == RAY_B200_KERNEL_WARPQUEUE) {
+    const int k = ctx->cfg.wq_k == 1 ? 1 : 2;
+    const int64_t queues = (int64_t)ctx->cfg.wq_warps * (int64_t)wq_warp_bytes(k, wq_node_capacity(k, p->max_depth));
+    budget = (int64_t)ctx->max_smem_optin - queues - 512;
+    if (budget < 0) { set_error(ctx, "render: warp-queue kernel does not fit shared memory (depth %d, %d warps)", p->max_depth, ctx->cfg.wq_warps); return 1; }
+  }
   int64_t nodes_fit = std::max<int64_t>(0, budget / 64);
   P.smem_nodes = (int32_t)std::min<int64_t>(P.n_inner, nodes_fit);
   const int64_t left = budget - (int64_t)P.smem_nodes * 64;
@@ -216,9 +228,12 @@ int do_render(futhark_context *ctx, const RenderParams &P) {
   lc.smem_budget = ctx->cfg.smem_budget;
   lc.refill_min = ctx->cfg.refill_min;
   lc.tail_from = ctx->cfg.tail_from;
+  lc.wq_warps = ctx->cfg.wq_warps < 1 ? 1 : (ctx->cfg.wq_warps > 16 ? 16 : ctx->cfg.wq_warps);
+  lc.wq_k = ctx->cfg.wq_k == 1 ? 1 : 2;
   if (lc.kernel == RAY_B200_KERNEL_WAVEFRONT && ensure_wavefront(ctx, P.local_tiles * kTilePixels)) return 1;
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev_start, ctx->stream));
-  if (lc.kernel == RAY_B200_KERNEL_PERSISTENT) CUDA_TRY(ctx, cudaMemsetAsync(ctx->work_cursor, 0, sizeof(int32_t), ctx->stream));
+  if (lc.kernel == RAY_B200_KERNEL_PERSISTENT || lc.kernel == RAY_B200_KERNEL_WARPQUEUE)
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->work_cursor, 0, sizeof(int32_t), ctx->stream));
   launch_render(P, lc, &ctx->wf, ctx->stream, &ctx->launches);
   CUDA_TRY(ctx, cudaGetLastError());
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev_stop, ctx->stream));
@@ -292,6 +307,8 @@ int futhark_context_config_set_tuning_param(struct futhark_context_config *cfg, 
   else if (!strcmp(name, "smem_budget")) cfg->smem_budget = (int32_t)v;
   else if (!strcmp(name, "refill_min")) cfg->refill_min = (int32_t)v;
   else if (!strcmp(name, "tail_from")) cfg->tail_from = (int32_t)v;
+  else if (!strcmp(name, "wq_warps")) cfg->wq_warps = (int32_t)v;
+  else if (!strcmp(name, "wq_k")) cfg->wq_k = (int32_t)v;
   else if (!strcmp(name, "rank")) cfg->rank = (int32_t)v;
   else if (!strcmp(name, "world")) cfg->world = (int32_t)v;
   else return 1;
@@ -312,6 +329,8 @@ struct futhark_context *futhark_context_new(struct futhark_context_config *cfg) 
   ctx->cfg.smem_budget = env_int("RAY_SMEM_BUDGET", ctx->cfg.smem_budget);
   ctx->cfg.refill_min = env_int("RAY_REFILL_MIN", ctx->cfg.refill_min);
   ctx->cfg.tail_from = env_int("RAY_TAIL_FROM", ctx->cfg.tail_from);
+  ctx->cfg.wq_warps = env_int("RAY_WQ_WARPS", ctx->cfg.wq_warps);
+  ctx->cfg.wq_k = env_int("RAY_WQ_K", ctx->cfg.wq_k);
   memset(&ctx->wf, 0, sizeof ctx->wf);
 
   auto fail = [&](const char *what, cudaError_t e) {
@@ -605,7 +624,7 @@ int ray_b200_context_set_spp(struct futhark_context *ctx, int32_t spp) {
 }
 int ray_b200_context_set_kernel(struct futhark_context *ctx, int32_t k) {
   if (bad_ctx(ctx)) return 1;
-  if (k < RAY_B200_KERNEL_AUTO || k > RAY_B200_KERNEL_WAVEFRONT) { set_error(ctx, "unknown kernel %d", k); return 1; }
+  if (k < RAY_B200_KERNEL_AUTO || k > RAY_B200_KERNEL_WARPQUEUE) { set_error(ctx, "unknown kernel %d", k); return 1; }
   ctx->cfg.kernel = k;
   return 0;
 }

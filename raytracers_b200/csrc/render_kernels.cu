@@ -8,8 +8,7 @@
 // on ties (strict `<` at ray.fut:40 with a shrinking t_max, leaves folded in ascending order).  We
 // visit the same set with a left-first stack DFS over the BVH2C layout (scene_host.h): one node step
 // tests both children's boxes, ~half the dependent steps of the reference loop and no re-visits.
-// Left-first DFS also visits leaves in ascending index order, so the strict `<` reproduces the
-// reference's tie-break.
+// See find_closest for how leaf tests are decoupled from the walk and how ties are broken.
 #include "render_params.h"
 #include "device_math.cuh"
 
@@ -55,6 +54,31 @@ struct StagedScene {  // top of the tree (BFS prefix) + optionally all spheres i
 
 // ------------------------------------------------------------------ objs_hit, first half (ray.fut:76-82)
 // bvh_fold contains closest_hit (-1, 1e9): returns the winning leaf (or -1) and its t.
+//
+// Because the reference never prunes by the running closest t, node traversal and sphere tests are
+// independent: the walk only *collects* the leaves it reaches (a leaf child is recorded by its
+// parent's node step, no extra iteration) and the sphere tests run afterwards in a tight loop.  This
+// keeps a warp's lanes in the same loop body instead of ping-ponging between "descend" and "test
+// leaf".  Collected leaves are not in ascending order any more, so the reference's tie-break (strict
+// `<` while folding leaves in ascending index order = lowest index wins an exact t tie) is applied
+// explicitly.  sphere_t is evaluated against the ORIGINAL t_max = 1e9: the value sphere_hit returns
+// does not depend on the shrinking t_max, only whether it is accepted does (root2 >= root1, so when
+// root1 is rejected for being >= t_max, root2 is too).
+constexpr int kLeafBuf = 16;
+
+template <bool kCount, class Scene>
+__device__ __forceinline__ void test_leaves(const Scene &sc, const int *leaves, int &nl, const Ray &r, const RayInv &q,
+                                            int &best_j, float &best_t, WorkCounters &wc) {
+  for (int k = 0; k < nl; k++) {
+    const int li = leaves[k];
+    const float4 g = sc.sphere(li);
+    if (kCount) wc.leaf_tests++;
+    const float t = sphere_t(g.x, g.y, g.z, g.w, r, q.a, 0.1f, 1000000000.0f);  // closest_hit, ray.fut:78-81
+    if (t >= 0.0f && (t < best_t || (t == best_t && li < best_j))) { best_t = t; best_j = li; }
+  }
+  nl = 0;
+}
+
 template <bool kCount, class Scene>
 __device__ __forceinline__ void find_closest(const Scene &sc, const float *root_box, const Ray &r, const RayInv &q,
                                              int &best_j, float &best_t, WorkCounters &wc) {
@@ -62,58 +86,53 @@ __device__ __forceinline__ void find_closest(const Scene &sc, const float *root_
   best_t = 1000000000.0f;
   if (kCount) { wc.segments++; wc.box_tests++; }
   if (!box_hit(root_box[0], root_box[1], root_box[2], root_box[3], root_box[4], root_box[5], r, q)) return;
-  int stack[kStackSize];
-  int sp = 0;
+  int stack[kStackSize + 1];
+  int leaves[kLeafBuf];
+  int sp = 1, nl = 0;
+  stack[0] = kDone;  // popping the sentinel ends the walk
   int cur = 0;
-  for (;;) {
-    while (cur >= 0) {  // inner node: test both children's boxes
-      float4 q0, q1, q2, q3;
-      sc.node(cur, q0, q1, q2, q3);
-      const int lptr = __float_as_int(q0.w), rptr = __float_as_int(q1.w);
-      const bool hl = box_hit(q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, r, q);
-      const bool hr = box_hit(q2.x, q2.y, q2.z, q3.x, q3.y, q3.z, r, q);
-      if (kCount) { wc.node_steps++; wc.box_tests += (lptr >= 0) + (rptr >= 0); }
-      if (hl) {
-        if (hr) stack[sp++] = rptr;
-        cur = lptr;
-      } else if (hr) {
-        cur = rptr;
-      } else {
-        cur = sp ? stack[--sp] : kDone;
-      }
-    }
-    if (cur == kDone) break;
-    {  // leaf ~cur: closest_hit (ray.fut:78-81) = sphere_hit s r 0.1 t_best
-      const int li = ~cur;
-      const float4 g = sc.sphere(li);
-      if (kCount) wc.leaf_tests++;
-      const float t = sphere_t(g.x, g.y, g.z, g.w, r, q.a, 0.1f, best_t);
-      if (t >= 0.0f) { best_t = t; best_j = li; }
-    }
-    cur = sp ? stack[--sp] : kDone;
+  while (cur != kDone) {
+    if (nl > kLeafBuf - 2) test_leaves<kCount>(sc, leaves, nl, r, q, best_j, best_t, wc);
+    float4 q0, q1, q2, q3;
+    sc.node(cur, q0, q1, q2, q3);
+    const int lptr = __float_as_int(q0.w), rptr = __float_as_int(q1.w);
+    const bool hl = box_hit(q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, r, q);
+    const bool hr = box_hit(q2.x, q2.y, q2.z, q3.x, q3.y, q3.z, r, q);
+    const bool l_leaf = lptr < 0, r_leaf = rptr < 0;
+    if (kCount) { wc.node_steps++; wc.box_tests += !l_leaf + !r_leaf; }
+    // a leaf child has no box in the reference (bvh.fut:84): it is always visited -> record it
+    if (l_leaf) leaves[nl] = ~lptr;
+    nl += l_leaf;
+    if (r_leaf) leaves[nl] = ~rptr;
+    nl += r_leaf;
+    // inner children whose box is hit are walked: left first, right deferred on the stack
+    const bool tl = hl && !l_leaf, tr = hr && !r_leaf;
+    if (tl && tr) stack[sp] = rptr;
+    sp += (tl && tr);
+    int nxt = tl ? lptr : rptr;
+    if (!(tl || tr)) nxt = stack[--sp];
+    cur = nxt;
   }
+  test_leaves<kCount>(sc, leaves, nl, r, q, best_j, best_t, wc);
 }
 
 // ------------------------------------------------------------------ one ray_colour iteration (ray.fut:130-148)
-// Advances the path by one segment.  Returns true if the path continues (r/light updated), false if
-// it ended with `colour` set.  `depth` counts objs_hit calls so far (ray.fut:129).
-template <bool kCount, class Scene>
-__device__ __forceinline__ bool advance_path(const Scene &sc, const RenderParams &P, Ray &r, V3 &light, int &depth,
-                                             V3 &colour, WorkCounters &wc) {
-  const RayInv q = ray_invariants(r);
-  int j;
-  float tb;
-  find_closest<kCount>(sc, P.root_box, r, q, j, tb, wc);
+// The part of a ray_colour iteration after the closest-hit search: given the fold result (j, tb),
+// re-intersect, scatter or shade the sky.  `a` = dot r.d r.d.  Returns true if the path continues
+// (r/light/depth updated), false if it ended with `colour` set.
+template <class Scene>
+__device__ __forceinline__ bool shade_segment(const Scene &sc, const RenderParams &P, Ray &r, const float a, const int j,
+                                              const float tb, V3 &light, int &depth, V3 &colour) {
   if (j >= 0) {
     // objs_hit, second half (ray.fut:83-85): re-intersect the winner with t_min = 0, t_max = t_best + 1
     const float4 g = sc.sphere(j);
-    const float t = sphere_t(g.x, g.y, g.z, g.w, r, q.a, 0.0f, tb + 1.0f);
+    const float t = sphere_t(g.x, g.y, g.z, g.w, r, a, 0.0f, tb + 1.0f);
     if (t >= 0.0f) {
       const V3 c = v3(g.x, g.y, g.z);
       const V3 p = vadd(r.o, vscale(t, r.d));                       // point_at_param, ray.fut:14-15
       const V3 n = vscale(1.0f / g.w, vsub(p, c));                  // ray.fut:42-43
-      // scatter (ray.fut:119-124): reflect (normalise r.dir) hit.normal; norm r.dir = sqrt(dot d d) = sqrt(q.a)
-      const V3 unit = vscale(1.0f / sqrtf(q.a), r.d);
+      // scatter (ray.fut:119-124): reflect (normalise r.dir) hit.normal; norm r.dir = sqrt(dot d d) = sqrt(a)
+      const V3 unit = vscale(1.0f / sqrtf(a), r.d);
       const V3 refl = vsub(unit, vscale(2.0f * vdot(unit, n), n));  // ray.fut:116-117
       if (vdot(refl, n) > 0.0f) {
         const float4 col = __ldg(P.colour + j);
@@ -130,12 +149,23 @@ __device__ __forceinline__ bool advance_path(const Scene &sc, const RenderParams
     }
   }
   // miss: sky gradient (ray.fut:141-148)
-  const V3 unit = vscale(1.0f / sqrtf(q.a), r.d);
+  const V3 unit = vscale(1.0f / sqrtf(a), r.d);
   const float t = 0.5f * (unit.y + 1.0f);
   const float w1 = 1.0f - t;
   const V3 sky = v3(w1 * 1.0f + t * 0.5f, w1 * 1.0f + t * 0.7f, w1 * 1.0f + t * 1.0f);
   colour = vmul(light, sky);
   return false;
+}
+
+// One whole ray_colour iteration for a lane-owned path.  `depth` counts objs_hit calls so far (ray.fut:129).
+template <bool kCount, class Scene>
+__device__ __forceinline__ bool advance_path(const Scene &sc, const RenderParams &P, Ray &r, V3 &light, int &depth,
+                                             V3 &colour, WorkCounters &wc) {
+  const RayInv q = ray_invariants(r);
+  int j;
+  float tb;
+  find_closest<kCount>(sc, P.root_box, r, q, j, tb, wc);
+  return shade_segment(sc, P, r, q.a, j, tb, light, depth, colour);
 }
 
 // get_ray for sample s of pixel (row j, column i): ray.fut:150-154 with pixel j i -> trace_ray (height-j) i
@@ -442,6 +472,270 @@ __global__ void __launch_bounds__(256, 2) wavefront_bounce_kernel(const __grid_c
   }
 }
 
+// ====================================================================================== K3: warp work-queue
+// Dense traversal.  K1/K2 bind a lane to a ray for a whole segment, so a warp's SIMT efficiency is
+// mean/max of its lanes' traversal lengths (ncu: 6.5 of 32 lanes active on rgbbox).  The reference's
+// fold is order-free and never prunes by the running closest t, so a segment's traversal is just a
+// SET of independent (ray, node) box-test items and (ray, leaf) sphere-test items.  K3 therefore
+// binds lanes to ITEMS, not rays: every warp keeps R = 32*K rays in flight, their traversal items on
+// a warp-private LIFO in shared memory, and each iteration pops 32 items — whatever rays they belong
+// to — so every lane does one node step (two box tests) or one sphere test.  Children are pushed back
+// with ballot/popc compaction; a sphere hit is folded into its ray's 64-bit (t, leaf index) word with
+// atomicMin, which is exactly the reference's "smallest t, lowest leaf index on ties".  When the
+// stacks run dry every ray of the round has its closest hit; the owner lanes shade, bounce, move to
+// the next sample or claim new pixels from the global cursor, and the next round starts.
+//
+// Stack bound: items are pushed in reverse lane order, which keeps the LIFO sorted by tree depth
+// (deepest on top); then at most 64 items of any depth are live at once (children of one 32-item
+// batch), so R + 64*(max_depth+1) entries always suffice.  Leaf items are drained whenever 32 are
+// available, so that stack never holds more than 31 + 64.
+constexpr int kSlotShift = 26;                 // item = slot << 26 | index  (index < 2^26; R <= 64 slots)
+constexpr uint32_t kIndexMask = (1u << kSlotShift) - 1u;
+constexpr unsigned long long kNoHit = ~0ull;
+constexpr int kLeafStack = 128;
+
+template <int K, bool kAllNodes, bool kSpheres>
+__global__ void __launch_bounds__(512, 1) render_warpqueue_kernel(const __grid_constant__ RenderParams P, const int ncap) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const float4 *s_nodes, *s_geom;
+  stage_scene(P, smem_raw, s_nodes, s_geom);
+  const StagedScene<kAllNodes, kSpheres> sc{P.nodes, P.geom, s_nodes, s_geom, P.smem_nodes};
+
+  constexpr int R = 32 * K;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const unsigned gt_mask = lane == 31 ? 0u : ~((2u << lane) - 1u);
+  unsigned char *wbase = smem_raw + ((staging_bytes(P) + 127) & ~(size_t)127) + (size_t)warp * wq_warp_bytes(K, ncap);
+  float4 *ray_o = reinterpret_cast<float4 *>(wbase);   // {o.xyz, a = dot d d}
+  float4 *ray_i = ray_o + R;                           // {1/d.xyz, 0}
+  float4 *ray_d = ray_i + R;                           // {d.xyz, 0}
+  float4 *p_light = ray_d + R;                         // {light.rgb, bits(depth)}   owner lane only
+  float4 *p_sum = p_light + R;                         // {sum.rgb, bits(sample)}    owner lane only
+  unsigned long long *best = reinterpret_cast<unsigned long long *>(p_sum + R);  // (bits(t) << 32 | leaf) min-folded
+  int *p_item = reinterpret_cast<int *>(best + R);     // work item (pixel) of the slot, -1 = idle
+  uint32_t *lstk = reinterpret_cast<uint32_t *>(p_item + R);
+  uint32_t *nstk = lstk + kLeafStack;
+
+  const int total = (int)(P.local_tiles * kTilePixels);
+#pragma unroll
+  for (int k = 0; k < K; k++) p_item[lane + 32 * k] = -1;
+  bool exhausted = false;
+  int ntop = 0, ltop = 0;  // warp-uniform stack heights
+
+  for (;;) {
+    // ---------------------------------------------------------------- claim pixels for idle slots
+    unsigned trav = 0;  // bit k: slot lane+32k has a traversal in flight this round
+    for (int pass = 0; pass < 4; pass++) {
+      if (!exhausted) {
+        int my_idle = 0;
+#pragma unroll
+        for (int k = 0; k < K; k++) my_idle += p_item[lane + 32 * k] < 0;
+        int incl = my_idle;  // inclusive warp scan of the idle counts
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(kFullMask, incl, o);
+          if (lane >= o) incl += v;
+        }
+        const int cnt = __shfl_sync(kFullMask, incl, 31);
+        if (cnt) {
+          int base = 0;
+          if (lane == 0) base = atomicAdd(P.work_cursor, cnt);
+          base = __shfl_sync(kFullMask, base, 0);
+          int kk = base + incl - my_idle;
+#pragma unroll
+          for (int k = 0; k < K; k++) {
+            const int slot = lane + 32 * k;
+            if (p_item[slot] < 0) {
+              const int item = kk++;
+              int pi, pj;
+              if (item < total) {
+                if (item_pixel(P, item, pi, pj)) {
+                  const Ray r = primary_ray(P, pi, pj, 0);
+                  p_item[slot] = item;
+                  ray_o[slot] = make_float4(r.o.x, r.o.y, r.o.z, 0.0f);
+                  ray_d[slot] = make_float4(r.d.x, r.d.y, r.d.z, 0.0f);
+                  p_light[slot] = make_float4(1.0f, 1.0f, 1.0f, __int_as_float(0));
+                  p_sum[slot] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(0));
+                } else if (P.tile_major) {
+                  P.out_pix[item] = 0;
+                }
+              }
+            }
+          }
+          exhausted = base + cnt >= total;
+        }
+      }
+      // -------------------------------------------------------------- set up this round's segments
+      // Root box test by the owner lane; a root miss is shaded (sky) on the spot and the path moves on,
+      // so sky-only pixels never occupy a traversal round.
+#pragma unroll
+      for (int k = 0; k < K; k++) {
+        const int slot = lane + 32 * k;
+        bool go = false;
+        if (!((trav >> k) & 1u)) {
+          int item = p_item[slot];
+          while (item >= 0) {
+            const float4 ro = ray_o[slot], rd = ray_d[slot];
+            Ray r;
+            r.o = v3(ro.x, ro.y, ro.z);
+            r.d = v3(rd.x, rd.y, rd.z);
+            const RayInv q = ray_invariants(r);
+            if (box_hit(P.root_box[0], P.root_box[1], P.root_box[2], P.root_box[3], P.root_box[4], P.root_box[5], r, q)) {
+              ray_o[slot] = make_float4(ro.x, ro.y, ro.z, q.a);
+              ray_i[slot] = make_float4(q.ix, q.iy, q.iz, 0.0f);
+              best[slot] = kNoHit;
+              go = true;
+              break;
+            }
+            // miss (ray.fut:141-148), path ends
+            const float4 pl = p_light[slot];
+            V3 light = v3(pl.x, pl.y, pl.z), colour;
+            int depth = __float_as_int(pl.w);
+            shade_segment(sc, P, r, q.a, -1, 0.0f, light, depth, colour);
+            float4 ps = p_sum[slot];
+            int s = __float_as_int(ps.w);
+            const V3 sum = (s == 0) ? colour : vadd(v3(ps.x, ps.y, ps.z), colour);
+            s++;
+            int pi, pj;
+            item_pixel(P, item, pi, pj);
+            if (s < P.spp) {
+              const Ray nr = primary_ray(P, pi, pj, s);
+              ray_o[slot] = make_float4(nr.o.x, nr.o.y, nr.o.z, 0.0f);
+              ray_d[slot] = make_float4(nr.d.x, nr.d.y, nr.d.z, 0.0f);
+              p_light[slot] = make_float4(1.0f, 1.0f, 1.0f, __int_as_float(0));
+              p_sum[slot] = make_float4(sum.x, sum.y, sum.z, __int_as_float(s));
+            } else {
+              write_pixel(P, item, pi, pj, sum);
+              p_item[slot] = -1;
+              item = -1;
+            }
+          }
+        }
+        const unsigned m = __ballot_sync(kFullMask, go);
+        if (go) {
+          nstk[ntop + __popc(m & lt_mask)] = (uint32_t)slot << kSlotShift;  // (slot, root node 0)
+          trav |= 1u << k;
+        }
+        ntop += __popc(m);
+      }
+      // another claim pass only helps if some slot went idle and pixels remain
+      bool idle_left = false;
+#pragma unroll
+      for (int k = 0; k < K; k++) idle_left |= p_item[lane + 32 * k] < 0;
+      if (exhausted || !__any_sync(kFullMask, idle_left)) break;
+    }
+    __syncwarp();
+    if (ntop == 0) {
+      bool any_active = false;
+#pragma unroll
+      for (int k = 0; k < K; k++) any_active |= p_item[lane + 32 * k] >= 0;
+      if (exhausted && !__any_sync(kFullMask, any_active)) break;  // frame done for this warp
+      continue;                                                     // only sky / padding pixels so far: claim again
+    }
+
+    // ---------------------------------------------------------------- dense traversal of the round
+    while (ntop > 0 || ltop > 0) {
+      if (ltop >= 32 || ntop == 0) {
+        // ---- leaf batch: closest_hit (ray.fut:78-81) for 32 (ray, sphere) pairs
+        const int n = ltop < 32 ? ltop : 32;
+        if (lane < n) {
+          const uint32_t it = lstk[ltop - 1 - lane];
+          const int slot = (int)(it >> kSlotShift), li = (int)(it & kIndexMask);
+          const float4 ro = ray_o[slot], rd = ray_d[slot];
+          const float4 g = sc.sphere(li);
+          Ray r;
+          r.o = v3(ro.x, ro.y, ro.z);
+          r.d = v3(rd.x, rd.y, rd.z);
+          const float t = sphere_t(g.x, g.y, g.z, g.w, r, ro.w, 0.1f, 1000000000.0f);
+          if (t >= 0.0f) atomicMin(best + slot, ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)li);
+        }
+        ltop -= n;
+      } else {
+        // ---- node batch: one BVH2C node step (both children's boxes) for 32 (ray, node) pairs
+        const int n = ntop < 32 ? ntop : 32;
+        bool pl_node = false, pr_node = false, pl_leaf = false, pr_leaf = false;
+        uint32_t tag = 0;
+        int lptr = 0, rptr = 0;
+        if (lane < n) {
+          const uint32_t it = nstk[ntop - 1 - lane];
+          tag = it & ~kIndexMask;
+          const int slot = (int)(it >> kSlotShift), cur = (int)(it & kIndexMask);
+          const float4 ro = ray_o[slot], ri = ray_i[slot];
+          float4 q0, q1, q2, q3;
+          sc.node(cur, q0, q1, q2, q3);
+          Ray r;
+          r.o = v3(ro.x, ro.y, ro.z);
+          r.d = v3(0.0f, 0.0f, 0.0f);
+          RayInv q;
+          q.ix = ri.x; q.iy = ri.y; q.iz = ri.z; q.a = ro.w;
+          lptr = __float_as_int(q0.w);
+          rptr = __float_as_int(q1.w);
+          const bool hl = box_hit(q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, r, q);
+          const bool hr = box_hit(q2.x, q2.y, q2.z, q3.x, q3.y, q3.z, r, q);
+          pl_leaf = lptr < 0;          // a leaf child has no box in the reference: always visited
+          pr_leaf = rptr < 0;
+          pl_node = hl && !pl_leaf;
+          pr_node = hr && !pr_leaf;
+        }
+        __syncwarp();  // all pops have been read before anything is pushed over them
+        ntop -= n;
+        const unsigned bl = __ballot_sync(kFullMask, pl_node), br = __ballot_sync(kFullMask, pr_node);
+        const unsigned cl = __ballot_sync(kFullMask, pl_leaf), cr = __ballot_sync(kFullMask, pr_leaf);
+        // reverse lane order: lane 0 popped the top (deepest) item, its children go back on top
+        const int nb = ntop + __popc(bl & gt_mask) + __popc(br & gt_mask);
+        if (pr_node) nstk[nb] = tag | (uint32_t)rptr;
+        if (pl_node) nstk[nb + (pr_node ? 1 : 0)] = tag | (uint32_t)lptr;
+        ntop += __popc(bl) + __popc(br);
+        const int lb = ltop + __popc(cl & lt_mask) + __popc(cr & lt_mask);
+        if (pl_leaf) lstk[lb] = tag | (uint32_t)(~lptr);
+        if (pr_leaf) lstk[lb + (pl_leaf ? 1 : 0)] = tag | (uint32_t)(~rptr);
+        ltop += __popc(cl) + __popc(cr);
+      }
+      __syncwarp();
+    }
+
+    // ---------------------------------------------------------------- shade: owner lanes finish the segment
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      if (!((trav >> k) & 1u)) continue;
+      const int slot = lane + 32 * k;
+      const int item = p_item[slot];
+      const float4 ro = ray_o[slot], rd = ray_d[slot], pl = p_light[slot];
+      const unsigned long long b = best[slot];
+      Ray r;
+      r.o = v3(ro.x, ro.y, ro.z);
+      r.d = v3(rd.x, rd.y, rd.z);
+      V3 light = v3(pl.x, pl.y, pl.z), colour;
+      int depth = __float_as_int(pl.w);
+      const int j = b == kNoHit ? -1 : (int)(unsigned)(b & 0xffffffffu);
+      const float tb = __uint_as_float((unsigned)(b >> 32));
+      if (shade_segment(sc, P, r, ro.w, j, tb, light, depth, colour)) {
+        ray_o[slot] = make_float4(r.o.x, r.o.y, r.o.z, 0.0f);
+        ray_d[slot] = make_float4(r.d.x, r.d.y, r.d.z, 0.0f);
+        p_light[slot] = make_float4(light.x, light.y, light.z, __int_as_float(depth));
+      } else {
+        const float4 ps = p_sum[slot];
+        int s = __float_as_int(ps.w);
+        const V3 sum = (s == 0) ? colour : vadd(v3(ps.x, ps.y, ps.z), colour);
+        s++;
+        int pi, pj;
+        item_pixel(P, item, pi, pj);
+        if (s < P.spp) {
+          const Ray nr = primary_ray(P, pi, pj, s);
+          ray_o[slot] = make_float4(nr.o.x, nr.o.y, nr.o.z, 0.0f);
+          ray_d[slot] = make_float4(nr.d.x, nr.d.y, nr.d.z, 0.0f);
+          p_light[slot] = make_float4(1.0f, 1.0f, 1.0f, __int_as_float(0));
+          p_sum[slot] = make_float4(sum.x, sum.y, sum.z, __int_as_float(s));
+        } else {
+          write_pixel(P, item, pi, pj, sum);
+          p_item[slot] = -1;
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
 // ====================================================================================== de-tiling (multi-GPU)
 // gathered: [world][tiles_padded][32] as an NCCL gather of every rank's compact buffer lays it out.
 __global__ void detile_kernel(const int32_t *__restrict__ gathered, int32_t *__restrict__ out, int H, int W, int world,
@@ -458,8 +752,6 @@ __global__ void detile_kernel(const int32_t *__restrict__ gathered, int32_t *__r
 }  // namespace
 
 // ---------------------------------------------------------------------------------------- host launchers
-size_t staging_bytes(const RenderParams &p) { return 128 + (size_t)p.smem_nodes * 64 + (size_t)p.smem_spheres * 16; }
-
 cudaError_t configure_kernels(int max_dynamic_smem) {
   cudaError_t e;
 #define RAYB200_SET(k)                                                                          \
@@ -473,6 +765,14 @@ cudaError_t configure_kernels(int max_dynamic_smem) {
   RAYB200_SET((wavefront_bounce_kernel<true, false>));
   RAYB200_SET((wavefront_bounce_kernel<false, true>));
   RAYB200_SET((wavefront_bounce_kernel<false, false>));
+  RAYB200_SET((render_warpqueue_kernel<1, true, true>));
+  RAYB200_SET((render_warpqueue_kernel<1, true, false>));
+  RAYB200_SET((render_warpqueue_kernel<1, false, true>));
+  RAYB200_SET((render_warpqueue_kernel<1, false, false>));
+  RAYB200_SET((render_warpqueue_kernel<2, true, true>));
+  RAYB200_SET((render_warpqueue_kernel<2, true, false>));
+  RAYB200_SET((render_warpqueue_kernel<2, false, true>));
+  RAYB200_SET((render_warpqueue_kernel<2, false, false>));
 #undef RAYB200_SET
   return cudaSuccess;
 }
@@ -507,6 +807,26 @@ void launch_render(const RenderParams &p, const LaunchConfig &lc, const Wavefron
         (*launches)++;
       }
     }
+    return;
+  }
+  if (lc.kernel == 4) {  // RAY_B200_KERNEL_WARPQUEUE: one CTA per SM, wq_warps warps, 32*wq_k rays in flight per warp
+    const int k = lc.wq_k == 1 ? 1 : 2;
+    const int wthreads = 32 * lc.wq_warps;
+    const int ncap = wq_node_capacity(k, p.max_depth);
+    const size_t wsmem = ((staging_bytes(p) + 127) & ~(size_t)127) + (size_t)lc.wq_warps * wq_warp_bytes(k, ncap);
+    long long ctas = lc.sm_count;
+    const long long useful = (items + 32 * k * lc.wq_warps - 1) / (32 * k * lc.wq_warps);
+    if (ctas > useful) ctas = useful;
+#define RAYB200_WQ(KK, A, S) render_warpqueue_kernel<KK, A, S><<<(unsigned)ctas, wthreads, wsmem, stream>>>(p, ncap)
+    if (k == 1) {
+      if (all_nodes && sph) RAYB200_WQ(1, true, true); else if (all_nodes) RAYB200_WQ(1, true, false);
+      else if (sph) RAYB200_WQ(1, false, true); else RAYB200_WQ(1, false, false);
+    } else {
+      if (all_nodes && sph) RAYB200_WQ(2, true, true); else if (all_nodes) RAYB200_WQ(2, true, false);
+      else if (sph) RAYB200_WQ(2, false, true); else RAYB200_WQ(2, false, false);
+    }
+#undef RAYB200_WQ
+    (*launches)++;
     return;
   }
   // RAY_B200_KERNEL_PERSISTENT

@@ -19,6 +19,7 @@ struct RenderParams {
   int32_t n_inner, n_leaves;
   int32_t smem_nodes;    // first smem_nodes BFS nodes are staged in shared memory (persistent/wavefront kernels)
   int32_t smem_spheres;  // first smem_spheres sphere records staged (0 or n_leaves)
+  int32_t max_depth;     // depth of the deepest leaf (root = 0): bounds the traversal stacks
   float root_box[6];
   float cam[12];         // origin, llc, horizontal, vertical (ray.fut:88-91)
   // frame
@@ -56,6 +57,8 @@ struct LaunchConfig {
   int smem_budget;     // bytes of dynamic shared memory per CTA for BVH staging
   int refill_min;      // persistent kernel: refill when at least this many lanes are idle
   int tail_from;       // wavefront: see WavefrontBuffers
+  int wq_warps;        // warp-queue kernel: warps per CTA (one CTA per SM)
+  int wq_k;            // warp-queue kernel: rays in flight per warp = 32 * wq_k (1 or 2)
 };
 
 void launch_render(const RenderParams &p, const LaunchConfig &lc, const WavefrontBuffers *wf, cudaStream_t stream,
@@ -63,7 +66,16 @@ void launch_render(const RenderParams &p, const LaunchConfig &lc, const Wavefron
 void launch_count_work(const RenderParams &p, cudaStream_t stream, int64_t *launches);
 void launch_detile(const int32_t *gathered, int32_t *out, int64_t H, int64_t W, int32_t world, int64_t tiles_padded,
                    cudaStream_t stream, int64_t *launches);
-size_t staging_bytes(const RenderParams &p);
+// dynamic shared memory of the BVH staging area: [mbarrier, padded to 128 B][nodes][sphere records]
+__host__ __device__ inline size_t staging_bytes(const RenderParams &p) {
+  return 128 + (size_t)p.smem_nodes * 64 + (size_t)p.smem_spheres * 16;
+}
+// warp-queue kernel: node-stack capacity (proved bound, see render_kernels.cu) and per-warp / per-CTA bytes
+__host__ __device__ inline int wq_node_capacity(int k, int max_depth) { return 32 * k + 64 * (max_depth + 1); }
+__host__ __device__ inline size_t wq_warp_bytes(int k, int ncap) {
+  const size_t r = 32 * (size_t)k;
+  return ((r * (16 * 5 + 8 + 4) + 128 * 4 + (size_t)ncap * 4) + 127) & ~(size_t)127;
+}
 cudaError_t configure_kernels(int max_dynamic_smem);
 
 }  // namespace rayb200

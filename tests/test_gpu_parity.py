@@ -10,7 +10,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-KERNELS = ["mega", "persistent", "wavefront"]
+KERNELS = ["mega", "persistent", "wavefront", "warpqueue"]
 
 
 def sha(a):
@@ -74,6 +74,9 @@ def test_random_scene_global_memory_nodes(R, oracle):
     for budget in (1024, 16 * 1024, 200 * 1024):
         got = gpu_frame(R, "random", h, w, "persistent", n=n, seed=5, smem_budget=budget)
         assert_same(got, want, f"random {n} smem_budget={budget}")
+    for warps, k in ((16, 2), (8, 1), (4, 2), (1, 1)):
+        got = gpu_frame(R, "random", h, w, "warpqueue", n=n, seed=5, wq_warps=warps, wq_k=k)
+        assert_same(got, want, f"random {n} warpqueue warps={warps} k={k}")
 
 
 @pytest.mark.parametrize("kernel", KERNELS)

@@ -50,6 +50,8 @@ def main():
     ap.add_argument("--refill_min", default="8")
     ap.add_argument("--smem_budget", default="65536")
     ap.add_argument("--tail_from", default="8")
+    ap.add_argument("--wq_warps", default="16")
+    ap.add_argument("--wq_k", default="2")
     a = ap.parse_args()
     rows = []
     for cfg in a.configs.split(","):
@@ -62,6 +64,8 @@ def main():
                 grid = [("x", "x", "x")]
             elif kernel == "wavefront":
                 grid = itertools.product(a.blocks_per_sm.split(","), a.tail_from.split(","), a.smem_budget.split(","))
+            elif kernel == "warpqueue":
+                grid = itertools.product(a.wq_warps.split(","), a.wq_k.split(","), ["x"])
             else:
                 grid = itertools.product(a.blocks_per_sm.split(","), a.refill_min.split(","), a.smem_budget.split(","))
             for bps, rf, sb in grid:
@@ -69,6 +73,8 @@ def main():
                     tuning = {}
                 elif kernel == "wavefront":
                     tuning = dict(blocks_per_sm=int(bps), tail_from=int(rf), smem_budget=int(sb))
+                elif kernel == "warpqueue":
+                    tuning = dict(wq_warps=int(bps), wq_k=int(rf))
                 else:
                     tuning = dict(blocks_per_sm=int(bps), refill_min=int(rf), smem_budget=int(sb))
                 t0 = time.time()
