@@ -61,9 +61,10 @@ struct futhark_opaque_prepared_scene {
   Lbvh tree;        // Karras-order LBVH (host copy, for introspection and store)
   CameraRec cam;
   float root_box[6];
-  int32_t max_depth = 0;
-  float4 *d_nodes = nullptr, *d_geom = nullptr, *d_colour = nullptr;
-  unsigned char *pinned = nullptr;  // packed nodes | geom | colour in page-locked host memory (upload source)
+  int32_t max_depth = 0, root_ptr = 0;
+  int64_t stored_nodes = 0;
+  float4 *d_nodes = nullptr, *d_nodes_soa = nullptr, *d_geom = nullptr, *d_colour = nullptr;
+  unsigned char *pinned = nullptr;  // packed nodes | nodes_soa | geom | colour in page-locked host memory (upload source)
   size_t nodes_bytes = 0, geom_bytes = 0, colour_bytes = 0;
   int64_t n = 0;
 };
@@ -148,8 +149,9 @@ int fill_params(futhark_context *ctx, const futhark_opaque_prepared_scene *p, in
   if (p->max_depth > kStackSize - 1) { set_error(ctx, "render: BVH depth %d exceeds the traversal stack", p->max_depth); return 1; }
   if (ensure_offsets(ctx, spp)) return 1;
   memset(&P, 0, sizeof P);
-  P.nodes = p->d_nodes; P.geom = p->d_geom; P.colour = p->d_colour;
-  P.n_inner = (int32_t)(p->n - 1); P.n_leaves = (int32_t)p->n;
+  P.nodes = p->d_nodes; P.nodes_soa = p->d_nodes_soa; P.geom = p->d_geom; P.colour = p->d_colour;
+  P.n_inner = (int32_t)p->stored_nodes; P.n_leaves = (int32_t)p->n;
+  P.root_ptr = p->root_ptr;
   P.max_depth = p->max_depth;
   memcpy(P.root_box, p->root_box, sizeof P.root_box);
   // The camera depends on the aspect ratio w/h given to prepare_scene (ray.fut:243-244); render's own
@@ -244,18 +246,24 @@ int do_render(futhark_context *ctx, const RenderParams &P) {
 
 void free_prepared_device(futhark_opaque_prepared_scene *p) {
   if (p->d_nodes) cudaFree(p->d_nodes);
+  if (p->d_nodes_soa) cudaFree(p->d_nodes_soa);
   if (p->d_geom) cudaFree(p->d_geom);
   if (p->d_colour) cudaFree(p->d_colour);
   if (p->pinned) cudaFreeHost(p->pinned);
-  p->d_nodes = p->d_geom = p->d_colour = nullptr;
+  p->d_nodes = p->d_nodes_soa = p->d_geom = p->d_colour = nullptr;
   p->pinned = nullptr;
 }
 
 // Host -> device copy of the packed scene from page-locked memory (asynchronous on the context stream).
 int copy_prepared_h2d(futhark_context *ctx, futhark_opaque_prepared_scene *p) {
-  CUDA_TRY(ctx, cudaMemcpyAsync(p->d_nodes, p->pinned, p->nodes_bytes, cudaMemcpyHostToDevice, ctx->stream));
-  CUDA_TRY(ctx, cudaMemcpyAsync(p->d_geom, p->pinned + p->nodes_bytes, p->geom_bytes, cudaMemcpyHostToDevice, ctx->stream));
-  CUDA_TRY(ctx, cudaMemcpyAsync(p->d_colour, p->pinned + p->nodes_bytes + p->geom_bytes, p->colour_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  const unsigned char *src = p->pinned;
+  CUDA_TRY(ctx, cudaMemcpyAsync(p->d_nodes, src, p->nodes_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  src += p->nodes_bytes;
+  CUDA_TRY(ctx, cudaMemcpyAsync(p->d_nodes_soa, src, p->nodes_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  src += p->nodes_bytes;
+  CUDA_TRY(ctx, cudaMemcpyAsync(p->d_geom, src, p->geom_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  src += p->geom_bytes;
+  CUDA_TRY(ctx, cudaMemcpyAsync(p->d_colour, src, p->colour_bytes, cudaMemcpyHostToDevice, ctx->stream));
   return 0;
 }
 
@@ -264,15 +272,19 @@ int upload_prepared(futhark_context *ctx, futhark_opaque_prepared_scene *p) {
   pack_bvh(p->host, p->tree, pk);
   memcpy(p->root_box, pk.root_box, sizeof p->root_box);
   p->max_depth = pk.max_depth;
+  p->root_ptr = pk.root_ptr;
+  p->stored_nodes = (int64_t)(pk.nodes.size() / 4);
   p->n = p->tree.n;
   p->nodes_bytes = pk.nodes.size() * sizeof(F4);
   p->geom_bytes = pk.geom.size() * sizeof(F4);
   p->colour_bytes = pk.colour.size() * sizeof(F4);
-  CUDA_TRY(ctx, cudaMallocHost(&p->pinned, p->nodes_bytes + p->geom_bytes + p->colour_bytes));
+  CUDA_TRY(ctx, cudaMallocHost(&p->pinned, 2 * p->nodes_bytes + p->geom_bytes + p->colour_bytes + 64));
   memcpy(p->pinned, pk.nodes.data(), p->nodes_bytes);
-  memcpy(p->pinned + p->nodes_bytes, pk.geom.data(), p->geom_bytes);
-  memcpy(p->pinned + p->nodes_bytes + p->geom_bytes, pk.colour.data(), p->colour_bytes);
-  CUDA_TRY(ctx, cudaMalloc(&p->d_nodes, p->nodes_bytes));
+  memcpy(p->pinned + p->nodes_bytes, pk.nodes_soa.data(), p->nodes_bytes);
+  memcpy(p->pinned + 2 * p->nodes_bytes, pk.geom.data(), p->geom_bytes);
+  memcpy(p->pinned + 2 * p->nodes_bytes + p->geom_bytes, pk.colour.data(), p->colour_bytes);
+  CUDA_TRY(ctx, cudaMalloc(&p->d_nodes, p->nodes_bytes ? p->nodes_bytes : 64));
+  CUDA_TRY(ctx, cudaMalloc(&p->d_nodes_soa, p->nodes_bytes ? p->nodes_bytes : 64));
   CUDA_TRY(ctx, cudaMalloc(&p->d_geom, p->geom_bytes));
   CUDA_TRY(ctx, cudaMalloc(&p->d_colour, p->colour_bytes));
   return copy_prepared_h2d(ctx, p);  // completion: futhark_context_sync, or stream order for later renders
@@ -709,7 +721,7 @@ int ray_b200_prepared_reupload(struct futhark_context *ctx, struct futhark_opaqu
 }
 int64_t ray_b200_prepared_device_bytes(struct futhark_context *ctx, const struct futhark_opaque_prepared_scene *p) {
   (void)ctx;
-  return p ? (int64_t)(p->nodes_bytes + p->geom_bytes + p->colour_bytes) : -1;
+  return p ? (int64_t)(2 * p->nodes_bytes + p->geom_bytes + p->colour_bytes) : -1;
 }
 
 int ray_b200_render_into(struct futhark_context *ctx, int32_t *out_pix_dev, float *out_rgb_dev, int64_t h, int64_t w, int32_t spp,

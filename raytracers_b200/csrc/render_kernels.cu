@@ -41,9 +41,9 @@ struct StagedScene {  // top of the tree (BFS prefix) + optionally all spheres i
   const float4 *s_nodes, *s_geom;
   int smem_nodes;
   __device__ __forceinline__ void node(int cur, float4 &q0, float4 &q1, float4 &q2, float4 &q3) const {
-    if (kAllNodes || cur < smem_nodes) {
-      const float4 *p = s_nodes + 4 * cur;
-      q0 = p[0]; q1 = p[1]; q2 = p[2]; q3 = p[3];
+    if (kAllNodes || cur < smem_nodes) {  // component-major in shared memory: 16-B stride -> all 8 bank groups in play
+      const float4 *p = s_nodes + cur;
+      q0 = p[0]; q1 = p[smem_nodes]; q2 = p[2 * smem_nodes]; q3 = p[3 * smem_nodes];
     } else {
       const float4 *p = nodes + 4 * (size_t)cur;
       q0 = __ldg(p); q1 = __ldg(p + 1); q2 = __ldg(p + 2); q3 = __ldg(p + 3);
@@ -79,9 +79,23 @@ __device__ __forceinline__ void test_leaves(const Scene &sc, const int *leaves, 
   nl = 0;
 }
 
+// Records the leaves a child pointer stands for: single leaf ~i (no box in the reference: always
+// visited), or the folded leaf-pair parent ~(i | kPairBit) whose box was just tested (`hit`).
+__device__ __forceinline__ void record_leaves(const int ptr, const bool hit, int *leaves, int &nl) {
+  const int v = ~ptr;  // >= 0 for leaf codes
+  const bool pair = (v & kPairBit) != 0;
+  const int i = v & kLeafIndexMask;
+  const bool take = ptr < 0 && (hit || !pair);
+  if (take) leaves[nl] = i;
+  nl += take;
+  if (take && pair) leaves[nl] = i + 1;
+  nl += take && pair;
+}
+
 template <bool kCount, class Scene>
-__device__ __forceinline__ void find_closest(const Scene &sc, const float *root_box, const Ray &r, const RayInv &q,
+__device__ __forceinline__ void find_closest(const Scene &sc, const RenderParams &P, const Ray &r, const RayInv &q,
                                              int &best_j, float &best_t, WorkCounters &wc) {
+  const float *root_box = P.root_box;
   best_j = -1;
   best_t = 1000000000.0f;
   if (kCount) { wc.segments++; wc.box_tests++; }
@@ -90,23 +104,26 @@ __device__ __forceinline__ void find_closest(const Scene &sc, const float *root_
   int leaves[kLeafBuf];
   int sp = 1, nl = 0;
   stack[0] = kDone;  // popping the sentinel ends the walk
-  int cur = 0;
+  int cur = P.root_ptr;
+  if (cur < 0) {     // two-sphere scene: the root is a folded leaf pair
+    record_leaves(cur, true, leaves, nl);
+    cur = kDone;
+  }
   while (cur != kDone) {
-    if (nl > kLeafBuf - 2) test_leaves<kCount>(sc, leaves, nl, r, q, best_j, best_t, wc);
+    if (nl > kLeafBuf - 4) test_leaves<kCount>(sc, leaves, nl, r, q, best_j, best_t, wc);
     float4 q0, q1, q2, q3;
     sc.node(cur, q0, q1, q2, q3);
     const int lptr = __float_as_int(q0.w), rptr = __float_as_int(q1.w);
     const bool hl = box_hit(q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, r, q);
     const bool hr = box_hit(q2.x, q2.y, q2.z, q3.x, q3.y, q3.z, r, q);
-    const bool l_leaf = lptr < 0, r_leaf = rptr < 0;
-    if (kCount) { wc.node_steps++; wc.box_tests += !l_leaf + !r_leaf; }
-    // a leaf child has no box in the reference (bvh.fut:84): it is always visited -> record it
-    if (l_leaf) leaves[nl] = ~lptr;
-    nl += l_leaf;
-    if (r_leaf) leaves[nl] = ~rptr;
-    nl += r_leaf;
+    if (kCount) {  // boxes the reference tests here: inner children and folded leaf-pair parents (not single leaves)
+      wc.node_steps++;
+      wc.box_tests += (lptr >= 0 || ((~lptr) & kPairBit)) + (rptr >= 0 || ((~rptr) & kPairBit));
+    }
+    record_leaves(lptr, hl, leaves, nl);
+    record_leaves(rptr, hr, leaves, nl);
     // inner children whose box is hit are walked: left first, right deferred on the stack
-    const bool tl = hl && !l_leaf, tr = hr && !r_leaf;
+    const bool tl = hl && lptr >= 0, tr = hr && rptr >= 0;
     if (tl && tr) stack[sp] = rptr;
     sp += (tl && tr);
     int nxt = tl ? lptr : rptr;
@@ -164,7 +181,7 @@ __device__ __forceinline__ bool advance_path(const Scene &sc, const RenderParams
   const RayInv q = ray_invariants(r);
   int j;
   float tb;
-  find_closest<kCount>(sc, P.root_box, r, q, j, tb, wc);
+  find_closest<kCount>(sc, P, r, q, j, tb, wc);
   return shade_segment(sc, P, r, q.a, j, tb, light, depth, colour);
 }
 
@@ -297,9 +314,13 @@ __device__ __forceinline__ void stage_scene(const RenderParams &P, unsigned char
   if (threadIdx.x == 0) {
     mbar_expect_tx(bar, node_bytes + geom_bytes);
     constexpr uint32_t kChunk = 32768;
-    for (uint32_t off = 0; off < node_bytes; off += kChunk)
-      tma_bulk_g2s(reinterpret_cast<unsigned char *>(nodes_dst) + off, reinterpret_cast<const unsigned char *>(P.nodes) + off,
-                   min(kChunk, node_bytes - off), bar);
+    // component-major: the first smem_nodes entries of each of the four component arrays
+    const uint32_t comp_bytes = (uint32_t)P.smem_nodes * 16u;
+    for (int c = 0; c < 4; c++)
+      for (uint32_t off = 0; off < comp_bytes; off += kChunk)
+        tma_bulk_g2s(reinterpret_cast<unsigned char *>(nodes_dst + (size_t)c * P.smem_nodes) + off,
+                     reinterpret_cast<const unsigned char *>(P.nodes_soa + (size_t)c * P.n_inner) + off,
+                     min(kChunk, comp_bytes - off), bar);
     for (uint32_t off = 0; off < geom_bytes; off += kChunk)
       tma_bulk_g2s(reinterpret_cast<unsigned char *>(geom_dst) + off, reinterpret_cast<const unsigned char *>(P.geom) + off,
                    min(kChunk, geom_bytes - off), bar);
@@ -492,7 +513,7 @@ __global__ void __launch_bounds__(256, 2) wavefront_bounce_kernel(const __grid_c
 constexpr int kSlotShift = 26;                 // item = slot << 26 | index  (index < 2^26; R <= 64 slots)
 constexpr uint32_t kIndexMask = (1u << kSlotShift) - 1u;
 constexpr unsigned long long kNoHit = ~0ull;
-constexpr int kLeafStack = 128;
+constexpr int kLeafStack = 192;  // <= 31 left over + 4 leaves x 32 lanes per node batch
 
 template <int K, bool kAllNodes, bool kSpheres>
 __global__ void __launch_bounds__(512, 1) render_warpqueue_kernel(const __grid_constant__ RenderParams P, const int ncap) {
@@ -612,11 +633,19 @@ __global__ void __launch_bounds__(512, 1) render_warpqueue_kernel(const __grid_c
           }
         }
         const unsigned m = __ballot_sync(kFullMask, go);
-        if (go) {
-          nstk[ntop + __popc(m & lt_mask)] = (uint32_t)slot << kSlotShift;  // (slot, root node 0)
-          trav |= 1u << k;
+        if (go) trav |= 1u << k;
+        if (P.root_ptr >= 0) {
+          if (go) nstk[ntop + __popc(m & lt_mask)] = (uint32_t)slot << kSlotShift;  // (slot, root node 0)
+          ntop += __popc(m);
+        } else {  // two-sphere scene: the root is a folded leaf pair -> straight to the sphere tests
+          const int li = (~P.root_ptr) & kLeafIndexMask;
+          if (go) {
+            const int lb = ltop + 2 * __popc(m & lt_mask);
+            lstk[lb] = ((uint32_t)slot << kSlotShift) | (uint32_t)li;
+            lstk[lb + 1] = ((uint32_t)slot << kSlotShift) | (uint32_t)(li + 1);
+          }
+          ltop += 2 * __popc(m);
         }
-        ntop += __popc(m);
       }
       // another claim pass only helps if some slot went idle and pixels remain
       bool idle_left = false;
@@ -625,7 +654,7 @@ __global__ void __launch_bounds__(512, 1) render_warpqueue_kernel(const __grid_c
       if (exhausted || !__any_sync(kFullMask, idle_left)) break;
     }
     __syncwarp();
-    if (ntop == 0) {
+    if (ntop == 0 && ltop == 0) {
       bool any_active = false;
 #pragma unroll
       for (int k = 0; k < K; k++) any_active |= p_item[lane + 32 * k] >= 0;
@@ -647,15 +676,20 @@ __global__ void __launch_bounds__(512, 1) render_warpqueue_kernel(const __grid_c
           r.o = v3(ro.x, ro.y, ro.z);
           r.d = v3(rd.x, rd.y, rd.z);
           const float t = sphere_t(g.x, g.y, g.z, g.w, r, ro.w, 0.1f, 1000000000.0f);
-          if (t >= 0.0f) atomicMin(best + slot, ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)li);
+          if (t >= 0.0f) {
+            // best only ever decreases, so a (possibly stale) plain read that is already <= key proves the atomic useless
+            const unsigned long long key = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)li;
+            if (key < *reinterpret_cast<volatile unsigned long long *>(best + slot)) atomicMin(best + slot, key);
+          }
         }
         ltop -= n;
       } else {
         // ---- node batch: one BVH2C node step (both children's boxes) for 32 (ray, node) pairs
         const int n = ntop < 32 ? ntop : 32;
-        bool pl_node = false, pr_node = false, pl_leaf = false, pr_leaf = false;
+        bool pl_node = false, pr_node = false;
         uint32_t tag = 0;
-        int lptr = 0, rptr = 0;
+        int lptr = 0, rptr = 0, nleaf = 0;
+        int lf0 = 0, lf1 = 0, lf2 = 0, lf3 = 0;  // up to 4 leaves reached by this item (registers, no local array)
         if (lane < n) {
           const uint32_t it = nstk[ntop - 1 - lane];
           tag = it & ~kIndexMask;
@@ -672,24 +706,37 @@ __global__ void __launch_bounds__(512, 1) render_warpqueue_kernel(const __grid_c
           rptr = __float_as_int(q1.w);
           const bool hl = box_hit(q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, r, q);
           const bool hr = box_hit(q2.x, q2.y, q2.z, q3.x, q3.y, q3.z, r, q);
-          pl_leaf = lptr < 0;          // a leaf child has no box in the reference: always visited
-          pr_leaf = rptr < 0;
-          pl_node = hl && !pl_leaf;
-          pr_node = hr && !pr_leaf;
+          pl_node = hl && lptr >= 0;
+          pr_node = hr && rptr >= 0;
+          // single leaf ~i: always visited; folded leaf pair ~(i | kPairBit): visited if its box is hit
+          const int lv = ~lptr, rv = ~rptr;
+          const bool lpair = (lv & kPairBit) != 0, rpair = (rv & kPairBit) != 0;
+          const bool ltake = lptr < 0 && (hl || !lpair), rtake = rptr < 0 && (hr || !rpair);
+          const int li0 = lv & kLeafIndexMask, ri0 = rv & kLeafIndexMask;
+          const int nl_l = ltake ? (lpair ? 2 : 1) : 0, nl_r = rtake ? (rpair ? 2 : 1) : 0;
+          nleaf = nl_l + nl_r;
+          lf0 = ltake ? li0 : ri0;
+          lf1 = nl_l == 2 ? li0 + 1 : (nl_l == 1 ? ri0 : ri0 + 1);
+          lf2 = nl_l == 2 ? ri0 : ri0 + 1;
+          lf3 = ri0 + 1;
         }
         __syncwarp();  // all pops have been read before anything is pushed over them
         ntop -= n;
         const unsigned bl = __ballot_sync(kFullMask, pl_node), br = __ballot_sync(kFullMask, pr_node);
-        const unsigned cl = __ballot_sync(kFullMask, pl_leaf), cr = __ballot_sync(kFullMask, pr_leaf);
         // reverse lane order: lane 0 popped the top (deepest) item, its children go back on top
         const int nb = ntop + __popc(bl & gt_mask) + __popc(br & gt_mask);
         if (pr_node) nstk[nb] = tag | (uint32_t)rptr;
         if (pl_node) nstk[nb + (pr_node ? 1 : 0)] = tag | (uint32_t)lptr;
         ntop += __popc(bl) + __popc(br);
-        const int lb = ltop + __popc(cl & lt_mask) + __popc(cr & lt_mask);
-        if (pl_leaf) lstk[lb] = tag | (uint32_t)(~lptr);
-        if (pr_leaf) lstk[lb + (pl_leaf ? 1 : 0)] = tag | (uint32_t)(~rptr);
-        ltop += __popc(cl) + __popc(cr);
+        // 0..4 leaf items per lane: exclusive scan from the bit planes of the count
+        const unsigned c0 = __ballot_sync(kFullMask, nleaf & 1), c1 = __ballot_sync(kFullMask, nleaf & 2),
+                       c2 = __ballot_sync(kFullMask, nleaf & 4);
+        const int lb = ltop + __popc(c0 & lt_mask) + 2 * __popc(c1 & lt_mask) + 4 * __popc(c2 & lt_mask);
+        if (nleaf > 0) lstk[lb] = tag | (uint32_t)lf0;
+        if (nleaf > 1) lstk[lb + 1] = tag | (uint32_t)lf1;
+        if (nleaf > 2) lstk[lb + 2] = tag | (uint32_t)lf2;
+        if (nleaf > 3) lstk[lb + 3] = tag | (uint32_t)lf3;
+        ltop += __popc(c0) + 2 * __popc(c1) + 4 * __popc(c2);
       }
       __syncwarp();
     }

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 
+#include "bvh_layout.h"
+
 namespace rayb200 {
 
 constexpr int kTileW = 8;       // a warp renders an 8x4-pixel tile (coherent primary rays, 128-B stores)
@@ -13,10 +15,12 @@ constexpr int kStackSize = 64;  // a radix tree over (32-bit key, 32-bit index) 
 
 struct RenderParams {
   // prepared scene (device layout of scene_host.h PackedBvh)
-  const float4 *nodes;
+  const float4 *nodes;      // node-major records (global fetch path)
+  const float4 *nodes_soa;  // component-major copy (source of the shared-memory staging)
   const float4 *geom;
   const float4 *colour;
-  int32_t n_inner, n_leaves;
+  int32_t n_inner, n_leaves;   // n_inner = STORED nodes (leaf-pair parents are folded away, scene_host.h)
+  int32_t root_ptr;            // 0, or a leaf-pair code when the scene has exactly 2 spheres
   int32_t smem_nodes;    // first smem_nodes BFS nodes are staged in shared memory (persistent/wavefront kernels)
   int32_t smem_spheres;  // first smem_spheres sphere records staged (0 or n_leaves)
   int32_t max_depth;     // depth of the deepest leaf (root = 0): bounds the traversal stacks
