@@ -26,7 +26,7 @@ struct futhark_context_config {
   int32_t kernel = RAY_B200_KERNEL_AUTO;
   int32_t rank = 0, world = 1;
   int32_t block_threads = 256, blocks_per_sm = 4, smem_budget = 48 * 1024, refill_min = 8, tail_from = 8;
-  int32_t wq_warps = 16, wq_k = 2;
+  int32_t wq_warps = 16, wq_k = 1, wq_spread = 1;
   std::string cache_file;
 };
 
@@ -45,6 +45,8 @@ struct futhark_context {
   int32_t offsets_spp = 0;
   int64_t launches = 0;
   WavefrontBuffers wf;                      // ray queues of the wavefront kernel (grown on demand)
+  float4 *sample_buf = nullptr;             // warp-queue kernel, spp > 1: per-warp finished-sample colours
+  size_t sample_buf_bytes = 0;
   bool profiling_paused = false;
   double total_render_ms = 0.0;
   int64_t renders = 0;
@@ -61,8 +63,7 @@ struct futhark_opaque_prepared_scene {
   Lbvh tree;        // Karras-order LBVH (host copy, for introspection and store)
   CameraRec cam;
   float root_box[6];
-  int32_t max_depth = 0, root_ptr = 0;
-  int64_t stored_nodes = 0;
+  int32_t max_depth = 0;
   float4 *d_nodes = nullptr, *d_nodes_soa = nullptr, *d_geom = nullptr, *d_colour = nullptr;
   unsigned char *pinned = nullptr;  // packed nodes | nodes_soa | geom | colour in page-locked host memory (upload source)
   size_t nodes_bytes = 0, geom_bytes = 0, colour_bytes = 0;
@@ -114,7 +115,7 @@ int parse_kernel(const char *v, int dflt) {
   return atoi(v);
 }
 
-const char *kTuningNames[] = {"kernel", "spp", "blocks_per_sm", "smem_budget", "refill_min", "tail_from", "wq_warps", "wq_k", "rank", "world"};
+const char *kTuningNames[] = {"kernel", "spp", "blocks_per_sm", "smem_budget", "refill_min", "tail_from", "wq_warps", "wq_k", "wq_spread", "rank", "world"};
 constexpr int kNumTuning = sizeof(kTuningNames) / sizeof(kTuningNames[0]);
 
 bool bad_ctx(futhark_context *ctx) { return ctx == nullptr || !ctx->ok; }
@@ -150,8 +151,7 @@ int fill_params(futhark_context *ctx, const futhark_opaque_prepared_scene *p, in
   if (ensure_offsets(ctx, spp)) return 1;
   memset(&P, 0, sizeof P);
   P.nodes = p->d_nodes; P.nodes_soa = p->d_nodes_soa; P.geom = p->d_geom; P.colour = p->d_colour;
-  P.n_inner = (int32_t)p->stored_nodes; P.n_leaves = (int32_t)p->n;
-  P.root_ptr = p->root_ptr;
+  P.n_inner = (int32_t)(p->n - 1); P.n_leaves = (int32_t)p->n;
   P.max_depth = p->max_depth;
   memcpy(P.root_box, p->root_box, sizeof P.root_box);
   // The camera depends on the aspect ratio w/h given to prepare_scene (ray.fut:243-244); render's own
@@ -171,7 +171,8 @@ int fill_params(futhark_context *ctx, const futhark_opaque_prepared_scene *p, in
   int64_t budget = std::min<int64_t>(ctx->cfg.smem_budget, ctx->max_smem_optin - 1024) - 128;
   if (resolve_kernel(ctx) == RAY_B200_KERNEL_WARPQUEUE) {
     const int k = ctx->cfg.wq_k == 1 ? 1 : 2;
-    const int64_t queues = (int64_t)ctx->cfg.wq_warps * (int64_t)wq_warp_bytes(k, wq_node_capacity(k, p->max_depth));
+    const int64_t wq_w = ctx->cfg.wq_warps < 1 ? 1 : (ctx->cfg.wq_warps > 24 ? 24 : ctx->cfg.wq_warps);
+    const int64_t queues = wq_w * (int64_t)wq_warp_bytes(k, wq_node_capacity(k, p->max_depth));
     budget = (int64_t)ctx->max_smem_optin - queues - 512;
     if (budget < 0) { set_error(ctx, "render: warp-queue kernel does not fit shared memory (depth %d, %d warps)", p->max_depth, ctx->cfg.wq_warps); return 1; }
   }
@@ -221,7 +222,7 @@ int ensure_wavefront(futhark_context *ctx, int64_t items) {
   return 0;
 }
 
-int do_render(futhark_context *ctx, const RenderParams &P) {
+int do_render(futhark_context *ctx, RenderParams &P) {
   LaunchConfig lc;
   lc.kernel = resolve_kernel(ctx);
   lc.block_threads = ctx->cfg.block_threads;
@@ -230,9 +231,22 @@ int do_render(futhark_context *ctx, const RenderParams &P) {
   lc.smem_budget = ctx->cfg.smem_budget;
   lc.refill_min = ctx->cfg.refill_min;
   lc.tail_from = ctx->cfg.tail_from;
-  lc.wq_warps = ctx->cfg.wq_warps < 1 ? 1 : (ctx->cfg.wq_warps > 16 ? 16 : ctx->cfg.wq_warps);
+  lc.wq_warps = ctx->cfg.wq_warps < 1 ? 1 : (ctx->cfg.wq_warps > 24 ? 24 : ctx->cfg.wq_warps);
   lc.wq_k = ctx->cfg.wq_k == 1 ? 1 : 2;
   if (lc.kernel == RAY_B200_KERNEL_WAVEFRONT && ensure_wavefront(ctx, P.local_tiles * kTilePixels)) return 1;
+  P.sample_buf = nullptr;
+  if (lc.kernel == RAY_B200_KERNEL_WARPQUEUE && P.spp > 1 && P.spp <= 65535 && ctx->cfg.wq_spread) {
+    // samples of a pixel are spread over a warp's slots; finished colours wait here for the in-order sum
+    const size_t need = (size_t)lc.sm_count * lc.wq_warps * kWqRing * (size_t)P.spp * sizeof(float4);
+    if (need > ctx->sample_buf_bytes) {
+      CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+      if (ctx->sample_buf) CUDA_TRY(ctx, cudaFree(ctx->sample_buf));
+      ctx->sample_buf = nullptr; ctx->sample_buf_bytes = 0;
+      CUDA_TRY(ctx, cudaMalloc(&ctx->sample_buf, need));
+      ctx->sample_buf_bytes = need;
+    }
+    P.sample_buf = ctx->sample_buf;
+  }
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev_start, ctx->stream));
   if (lc.kernel == RAY_B200_KERNEL_PERSISTENT || lc.kernel == RAY_B200_KERNEL_WARPQUEUE)
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->work_cursor, 0, sizeof(int32_t), ctx->stream));
@@ -272,8 +286,6 @@ int upload_prepared(futhark_context *ctx, futhark_opaque_prepared_scene *p) {
   pack_bvh(p->host, p->tree, pk);
   memcpy(p->root_box, pk.root_box, sizeof p->root_box);
   p->max_depth = pk.max_depth;
-  p->root_ptr = pk.root_ptr;
-  p->stored_nodes = (int64_t)(pk.nodes.size() / 4);
   p->n = p->tree.n;
   p->nodes_bytes = pk.nodes.size() * sizeof(F4);
   p->geom_bytes = pk.geom.size() * sizeof(F4);
@@ -283,8 +295,8 @@ int upload_prepared(futhark_context *ctx, futhark_opaque_prepared_scene *p) {
   memcpy(p->pinned + p->nodes_bytes, pk.nodes_soa.data(), p->nodes_bytes);
   memcpy(p->pinned + 2 * p->nodes_bytes, pk.geom.data(), p->geom_bytes);
   memcpy(p->pinned + 2 * p->nodes_bytes + p->geom_bytes, pk.colour.data(), p->colour_bytes);
-  CUDA_TRY(ctx, cudaMalloc(&p->d_nodes, p->nodes_bytes ? p->nodes_bytes : 64));
-  CUDA_TRY(ctx, cudaMalloc(&p->d_nodes_soa, p->nodes_bytes ? p->nodes_bytes : 64));
+  CUDA_TRY(ctx, cudaMalloc(&p->d_nodes, p->nodes_bytes));
+  CUDA_TRY(ctx, cudaMalloc(&p->d_nodes_soa, p->nodes_bytes));
   CUDA_TRY(ctx, cudaMalloc(&p->d_geom, p->geom_bytes));
   CUDA_TRY(ctx, cudaMalloc(&p->d_colour, p->colour_bytes));
   return copy_prepared_h2d(ctx, p);  // completion: futhark_context_sync, or stream order for later renders
@@ -321,6 +333,7 @@ int futhark_context_config_set_tuning_param(struct futhark_context_config *cfg, 
   else if (!strcmp(name, "tail_from")) cfg->tail_from = (int32_t)v;
   else if (!strcmp(name, "wq_warps")) cfg->wq_warps = (int32_t)v;
   else if (!strcmp(name, "wq_k")) cfg->wq_k = (int32_t)v;
+  else if (!strcmp(name, "wq_spread")) cfg->wq_spread = (int32_t)v;
   else if (!strcmp(name, "rank")) cfg->rank = (int32_t)v;
   else if (!strcmp(name, "world")) cfg->world = (int32_t)v;
   else return 1;
@@ -343,6 +356,7 @@ struct futhark_context *futhark_context_new(struct futhark_context_config *cfg) 
   ctx->cfg.tail_from = env_int("RAY_TAIL_FROM", ctx->cfg.tail_from);
   ctx->cfg.wq_warps = env_int("RAY_WQ_WARPS", ctx->cfg.wq_warps);
   ctx->cfg.wq_k = env_int("RAY_WQ_K", ctx->cfg.wq_k);
+  ctx->cfg.wq_spread = env_int("RAY_WQ_SPREAD", ctx->cfg.wq_spread);
   memset(&ctx->wf, 0, sizeof ctx->wf);
 
   auto fail = [&](const char *what, cudaError_t e) {
@@ -387,6 +401,7 @@ void futhark_context_free(struct futhark_context *ctx) {
     cudaStreamSynchronize(ctx->stream);
   }
   if (ctx->ok) free_wavefront(ctx);
+  if (ctx->sample_buf) cudaFree(ctx->sample_buf);
   if (ctx->offsets) cudaFree(ctx->offsets);
   if (ctx->work_cursor) cudaFree(ctx->work_cursor);
   if (ctx->counters) cudaFree(ctx->counters);

@@ -79,23 +79,9 @@ __device__ __forceinline__ void test_leaves(const Scene &sc, const int *leaves, 
   nl = 0;
 }
 
-// Records the leaves a child pointer stands for: single leaf ~i (no box in the reference: always
-// visited), or the folded leaf-pair parent ~(i | kPairBit) whose box was just tested (`hit`).
-__device__ __forceinline__ void record_leaves(const int ptr, const bool hit, int *leaves, int &nl) {
-  const int v = ~ptr;  // >= 0 for leaf codes
-  const bool pair = (v & kPairBit) != 0;
-  const int i = v & kLeafIndexMask;
-  const bool take = ptr < 0 && (hit || !pair);
-  if (take) leaves[nl] = i;
-  nl += take;
-  if (take && pair) leaves[nl] = i + 1;
-  nl += take && pair;
-}
-
 template <bool kCount, class Scene>
-__device__ __forceinline__ void find_closest(const Scene &sc, const RenderParams &P, const Ray &r, const RayInv &q,
+__device__ __forceinline__ void find_closest(const Scene &sc, const float *root_box, const Ray &r, const RayInv &q,
                                              int &best_j, float &best_t, WorkCounters &wc) {
-  const float *root_box = P.root_box;
   best_j = -1;
   best_t = 1000000000.0f;
   if (kCount) { wc.segments++; wc.box_tests++; }
@@ -104,26 +90,23 @@ __device__ __forceinline__ void find_closest(const Scene &sc, const RenderParams
   int leaves[kLeafBuf];
   int sp = 1, nl = 0;
   stack[0] = kDone;  // popping the sentinel ends the walk
-  int cur = P.root_ptr;
-  if (cur < 0) {     // two-sphere scene: the root is a folded leaf pair
-    record_leaves(cur, true, leaves, nl);
-    cur = kDone;
-  }
+  int cur = 0;
   while (cur != kDone) {
-    if (nl > kLeafBuf - 4) test_leaves<kCount>(sc, leaves, nl, r, q, best_j, best_t, wc);
+    if (nl > kLeafBuf - 2) test_leaves<kCount>(sc, leaves, nl, r, q, best_j, best_t, wc);
     float4 q0, q1, q2, q3;
     sc.node(cur, q0, q1, q2, q3);
     const int lptr = __float_as_int(q0.w), rptr = __float_as_int(q1.w);
     const bool hl = box_hit(q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, r, q);
     const bool hr = box_hit(q2.x, q2.y, q2.z, q3.x, q3.y, q3.z, r, q);
-    if (kCount) {  // boxes the reference tests here: inner children and folded leaf-pair parents (not single leaves)
-      wc.node_steps++;
-      wc.box_tests += (lptr >= 0 || ((~lptr) & kPairBit)) + (rptr >= 0 || ((~rptr) & kPairBit));
-    }
-    record_leaves(lptr, hl, leaves, nl);
-    record_leaves(rptr, hr, leaves, nl);
+    const bool l_leaf = lptr < 0, r_leaf = rptr < 0;
+    if (kCount) { wc.node_steps++; wc.box_tests += !l_leaf + !r_leaf; }
+    // a leaf child has no box in the reference (bvh.fut:84): it is always visited -> record it
+    if (l_leaf) leaves[nl] = ~lptr;
+    nl += l_leaf;
+    if (r_leaf) leaves[nl] = ~rptr;
+    nl += r_leaf;
     // inner children whose box is hit are walked: left first, right deferred on the stack
-    const bool tl = hl && lptr >= 0, tr = hr && rptr >= 0;
+    const bool tl = hl && !l_leaf, tr = hr && !r_leaf;
     if (tl && tr) stack[sp] = rptr;
     sp += (tl && tr);
     int nxt = tl ? lptr : rptr;
@@ -181,7 +164,7 @@ __device__ __forceinline__ bool advance_path(const Scene &sc, const RenderParams
   const RayInv q = ray_invariants(r);
   int j;
   float tb;
-  find_closest<kCount>(sc, P, r, q, j, tb, wc);
+  find_closest<kCount>(sc, P.root_box, r, q, j, tb, wc);
   return shade_segment(sc, P, r, q.a, j, tb, light, depth, colour);
 }
 
@@ -503,20 +486,27 @@ __global__ void __launch_bounds__(256, 2) wavefront_bounce_kernel(const __grid_c
 // to — so every lane does one node step (two box tests) or one sphere test.  Children are pushed back
 // with ballot/popc compaction; a sphere hit is folded into its ray's 64-bit (t, leaf index) word with
 // atomicMin, which is exactly the reference's "smallest t, lowest leaf index on ties".  When the
-// stacks run dry every ray of the round has its closest hit; the owner lanes shade, bounce, move to
-// the next sample or claim new pixels from the global cursor, and the next round starts.
+// stacks run dry every ray of the round has its closest hit; the owner lanes shade, bounce, and idle
+// slots are refilled, and the next round starts.
 //
 // Stack bound: items are pushed in reverse lane order, which keeps the LIFO sorted by tree depth
 // (deepest on top); then at most 64 items of any depth are live at once (children of one 32-item
 // batch), so R + 64*(max_depth+1) entries always suffice.  Leaf items are drained whenever 32 are
 // available, so that stack never holds more than 31 + 64.
+//
+// Work distribution.  spp == 1 (kSpread = false): a slot owns a pixel (and, for robustness, all its
+// samples), claimed from the global cursor with one warp-aggregated atomicAdd.  spp > 1 (kSpread):
+// a warp opens up to kRing pixels at a time and hands their samples, in order, to whichever slots are
+// idle — consecutive lanes trace consecutive samples of the same pixel (coherent), the scheduling
+// grain is one sample instead of one pixel x spp (no long tails, scales to many GPUs), and every
+// finished sample's colour is parked in an L2-resident buffer so that the pixel is summed in SAMPLE
+// ORDER when its last sample lands, which keeps the result bit-identical to the sequential definition.
 constexpr int kSlotShift = 26;                 // item = slot << 26 | index  (index < 2^26; R <= 64 slots)
 constexpr uint32_t kIndexMask = (1u << kSlotShift) - 1u;
 constexpr unsigned long long kNoHit = ~0ull;
-constexpr int kLeafStack = 192;  // <= 31 left over + 4 leaves x 32 lanes per node batch
 
-template <int K, bool kAllNodes, bool kSpheres>
-__global__ void __launch_bounds__(512, 1) render_warpqueue_kernel(const __grid_constant__ RenderParams P, const int ncap) {
+template <int K, bool kSpread, bool kAllNodes, bool kSpheres>
+__global__ void __launch_bounds__(768, 1) render_warpqueue_kernel(const __grid_constant__ RenderParams P, const int ncap) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const float4 *s_nodes, *s_geom;
   stage_scene(P, smem_raw, s_nodes, s_geom);
@@ -531,43 +521,102 @@ __global__ void __launch_bounds__(512, 1) render_warpqueue_kernel(const __grid_c
   float4 *ray_i = ray_o + R;                           // {1/d.xyz, 0}
   float4 *ray_d = ray_i + R;                           // {d.xyz, 0}
   float4 *p_light = ray_d + R;                         // {light.rgb, bits(depth)}   owner lane only
-  float4 *p_sum = p_light + R;                         // {sum.rgb, bits(sample)}    owner lane only
+  float4 *p_sum = p_light + R;                         // {sum.rgb, bits(sample)} / spread: w = bits(ring << 16 | sample)
   unsigned long long *best = reinterpret_cast<unsigned long long *>(p_sum + R);  // (bits(t) << 32 | leaf) min-folded
   int *p_item = reinterpret_cast<int *>(best + R);     // work item (pixel) of the slot, -1 = idle
-  uint32_t *lstk = reinterpret_cast<uint32_t *>(p_item + R);
-  uint32_t *nstk = lstk + kLeafStack;
+  int *ring_item = p_item + R;                         // spread: pixel item of ring entry m
+  int *ring_done = ring_item + kWqRing;                // spread: samples finished, -1 = entry free
+  uint32_t *lstk = reinterpret_cast<uint32_t *>(ring_done + kWqRing);
+  uint32_t *nstk = lstk + kWqLeafStack;
 
   const int total = (int)(P.local_tiles * kTilePixels);
+  const int spp = P.spp;
 #pragma unroll
   for (int k = 0; k < K; k++) p_item[lane + 32 * k] = -1;
+  if (lane < kWqRing) ring_done[lane] = -1;
+  __syncwarp();
   bool exhausted = false;
-  int ntop = 0, ltop = 0;  // warp-uniform stack heights
+  int ntop = 0, ltop = 0;                      // warp-uniform stack heights
+  int open_seq = 0, disp_seq = 0, disp_s = 0;  // spread dispenser (warp-uniform): pixels opened / next sample to hand out
+  float4 *cbuf = nullptr;                      // spread: [kWqRing][spp] finished-sample colours of this warp
+  if (kSpread) cbuf = P.sample_buf + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * kWqRing * (size_t)spp;
+
+  // A path in `slot` has ended with `colour`.
+  auto finish_path = [&](const int slot, const V3 colour) {
+    if (kSpread) {
+      const int ms = __float_as_int(p_sum[slot].w);
+      __stcg(cbuf + (size_t)(ms >> 16) * spp + (ms & 0xffff), make_float4(colour.x, colour.y, colour.z, 0.0f));
+      atomicAdd(ring_done + (ms >> 16), 1);
+      p_item[slot] = -1;
+    } else {
+      const int item = p_item[slot];
+      const float4 ps = p_sum[slot];
+      int s = __float_as_int(ps.w);
+      const V3 sum = (s == 0) ? colour : vadd(v3(ps.x, ps.y, ps.z), colour);
+      s++;
+      int pi, pj;
+      item_pixel(P, item, pi, pj);
+      if (s < spp) {
+        const Ray nr = primary_ray(P, pi, pj, s);
+        ray_o[slot] = make_float4(nr.o.x, nr.o.y, nr.o.z, 0.0f);
+        ray_d[slot] = make_float4(nr.d.x, nr.d.y, nr.d.z, 0.0f);
+        p_light[slot] = make_float4(1.0f, 1.0f, 1.0f, __int_as_float(0));
+        p_sum[slot] = make_float4(sum.x, sum.y, sum.z, __int_as_float(s));
+      } else {
+        write_pixel(P, item, pi, pj, sum);
+        p_item[slot] = -1;
+      }
+    }
+  };
+  // spread: pixels whose last sample has landed are summed IN SAMPLE ORDER and written; frees the ring entry
+  auto finalize_pixels = [&]() {
+    __syncwarp();
+    if (lane < kWqRing && ring_done[lane] == spp) {
+      const int item = ring_item[lane];
+      int pi, pj;
+      if (item_pixel(P, item, pi, pj)) {
+        const float4 *c = cbuf + (size_t)lane * spp;
+        const float4 c0 = __ldcg(c);
+        V3 sum = v3(c0.x, c0.y, c0.z);
+        for (int s = 1; s < spp; s++) {
+          const float4 cs = __ldcg(c + s);
+          sum = vadd(sum, v3(cs.x, cs.y, cs.z));
+        }
+        write_pixel(P, item, pi, pj, sum);
+      } else if (P.tile_major) {
+        P.out_pix[item] = 0;
+      }
+      ring_done[lane] = -1;
+    }
+    __syncwarp();
+  };
 
   for (;;) {
-    // ---------------------------------------------------------------- claim pixels for idle slots
     unsigned trav = 0;  // bit k: slot lane+32k has a traversal in flight this round
     for (int pass = 0; pass < 4; pass++) {
-      if (!exhausted) {
-        int my_idle = 0;
+      // ---------------------------------------------------------------- hand work to idle slots
+      if (kSpread) finalize_pixels();
+      int my_idle = 0;
 #pragma unroll
-        for (int k = 0; k < K; k++) my_idle += p_item[lane + 32 * k] < 0;
-        int incl = my_idle;  // inclusive warp scan of the idle counts
+      for (int k = 0; k < K; k++) my_idle += p_item[lane + 32 * k] < 0;
+      int incl = my_idle;  // inclusive warp scan of the idle counts
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int v = __shfl_up_sync(kFullMask, incl, o);
-          if (lane >= o) incl += v;
-        }
-        const int cnt = __shfl_sync(kFullMask, incl, 31);
-        if (cnt) {
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(kFullMask, incl, o);
+        if (lane >= o) incl += v;
+      }
+      const int cnt = __shfl_sync(kFullMask, incl, 31);
+      int rank = incl - my_idle;
+      if (!kSpread) {
+        if (cnt && !exhausted) {
           int base = 0;
           if (lane == 0) base = atomicAdd(P.work_cursor, cnt);
           base = __shfl_sync(kFullMask, base, 0);
-          int kk = base + incl - my_idle;
 #pragma unroll
           for (int k = 0; k < K; k++) {
             const int slot = lane + 32 * k;
             if (p_item[slot] < 0) {
-              const int item = kk++;
+              const int item = base + rank++;
               int pi, pj;
               if (item < total) {
                 if (item_pixel(P, item, pi, pj)) {
@@ -585,17 +634,57 @@ __global__ void __launch_bounds__(512, 1) render_warpqueue_kernel(const __grid_c
           }
           exhausted = base + cnt >= total;
         }
+      } else if (cnt) {
+        int avail = (open_seq - disp_seq) * spp - disp_s;
+        while (!exhausted && avail < cnt) {  // open more pixels (one cursor claim each) while the ring has room
+          const int m = open_seq & (kWqRing - 1);
+          if (ring_done[m] != -1) break;
+          int item = 0;
+          if (lane == 0) item = atomicAdd(P.work_cursor, 1);
+          item = __shfl_sync(kFullMask, item, 0);
+          if (item >= total) { exhausted = true; break; }
+          if (lane == 0) { ring_item[m] = item; ring_done[m] = 0; }
+          __syncwarp();
+          open_seq++;
+          avail += spp;
+        }
+        const int give = cnt < avail ? cnt : avail;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+          const int slot = lane + 32 * k;
+          if (p_item[slot] < 0) {
+            const int rk = rank++;
+            if (rk < give) {
+              int s = disp_s + rk, seq = disp_seq;
+              while (s >= spp) { s -= spp; seq++; }
+              const int m = seq & (kWqRing - 1);
+              const int item = ring_item[m];
+              int pi, pj;
+              if (item_pixel(P, item, pi, pj)) {
+                const Ray r = primary_ray(P, pi, pj, s);
+                p_item[slot] = item;
+                ray_o[slot] = make_float4(r.o.x, r.o.y, r.o.z, 0.0f);
+                ray_d[slot] = make_float4(r.d.x, r.d.y, r.d.z, 0.0f);
+                p_light[slot] = make_float4(1.0f, 1.0f, 1.0f, __int_as_float(0));
+                p_sum[slot] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float((m << 16) | s));
+              } else {
+                atomicAdd(ring_done + m, 1);  // padding pixel of a partial tile: nothing to trace
+              }
+            }
+          }
+        }
+        disp_s += give;
+        while (disp_s >= spp) { disp_s -= spp; disp_seq++; }
       }
       // -------------------------------------------------------------- set up this round's segments
-      // Root box test by the owner lane; a root miss is shaded (sky) on the spot and the path moves on,
-      // so sky-only pixels never occupy a traversal round.
+      // Root box test by the owner lane; a root miss is shaded (sky) on the spot and the path ends,
+      // so sky rays never occupy a traversal round.
 #pragma unroll
       for (int k = 0; k < K; k++) {
         const int slot = lane + 32 * k;
         bool go = false;
         if (!((trav >> k) & 1u)) {
-          int item = p_item[slot];
-          while (item >= 0) {
+          while (p_item[slot] >= 0) {
             const float4 ro = ray_o[slot], rd = ray_d[slot];
             Ray r;
             r.o = v3(ro.x, ro.y, ro.z);
@@ -608,58 +697,38 @@ __global__ void __launch_bounds__(512, 1) render_warpqueue_kernel(const __grid_c
               go = true;
               break;
             }
-            // miss (ray.fut:141-148), path ends
-            const float4 pl = p_light[slot];
+            const float4 pl = p_light[slot];  // miss (ray.fut:141-148)
             V3 light = v3(pl.x, pl.y, pl.z), colour;
             int depth = __float_as_int(pl.w);
             shade_segment(sc, P, r, q.a, -1, 0.0f, light, depth, colour);
-            float4 ps = p_sum[slot];
-            int s = __float_as_int(ps.w);
-            const V3 sum = (s == 0) ? colour : vadd(v3(ps.x, ps.y, ps.z), colour);
-            s++;
-            int pi, pj;
-            item_pixel(P, item, pi, pj);
-            if (s < P.spp) {
-              const Ray nr = primary_ray(P, pi, pj, s);
-              ray_o[slot] = make_float4(nr.o.x, nr.o.y, nr.o.z, 0.0f);
-              ray_d[slot] = make_float4(nr.d.x, nr.d.y, nr.d.z, 0.0f);
-              p_light[slot] = make_float4(1.0f, 1.0f, 1.0f, __int_as_float(0));
-              p_sum[slot] = make_float4(sum.x, sum.y, sum.z, __int_as_float(s));
-            } else {
-              write_pixel(P, item, pi, pj, sum);
-              p_item[slot] = -1;
-              item = -1;
-            }
+            finish_path(slot, colour);
           }
         }
         const unsigned m = __ballot_sync(kFullMask, go);
-        if (go) trav |= 1u << k;
-        if (P.root_ptr >= 0) {
-          if (go) nstk[ntop + __popc(m & lt_mask)] = (uint32_t)slot << kSlotShift;  // (slot, root node 0)
-          ntop += __popc(m);
-        } else {  // two-sphere scene: the root is a folded leaf pair -> straight to the sphere tests
-          const int li = (~P.root_ptr) & kLeafIndexMask;
-          if (go) {
-            const int lb = ltop + 2 * __popc(m & lt_mask);
-            lstk[lb] = ((uint32_t)slot << kSlotShift) | (uint32_t)li;
-            lstk[lb + 1] = ((uint32_t)slot << kSlotShift) | (uint32_t)(li + 1);
-          }
-          ltop += 2 * __popc(m);
+        if (go) {
+          nstk[ntop + __popc(m & lt_mask)] = (uint32_t)slot << kSlotShift;  // (slot, root node 0)
+          trav |= 1u << k;
         }
+        ntop += __popc(m);
       }
-      // another claim pass only helps if some slot went idle and pixels remain
+      // another pass only helps if some slot is idle and there is still work to hand out
       bool idle_left = false;
 #pragma unroll
       for (int k = 0; k < K; k++) idle_left |= p_item[lane + 32 * k] < 0;
-      if (exhausted || !__any_sync(kFullMask, idle_left)) break;
+      const bool more = kSpread ? (!exhausted || (open_seq - disp_seq) * spp - disp_s > 0) : !exhausted;
+      if (!more || !__any_sync(kFullMask, idle_left)) break;
     }
     __syncwarp();
-    if (ntop == 0 && ltop == 0) {
+    if (ntop == 0) {
       bool any_active = false;
 #pragma unroll
       for (int k = 0; k < K; k++) any_active |= p_item[lane + 32 * k] >= 0;
-      if (exhausted && !__any_sync(kFullMask, any_active)) break;  // frame done for this warp
-      continue;                                                     // only sky / padding pixels so far: claim again
+      const bool undispensed = kSpread && (open_seq - disp_seq) * spp - disp_s > 0;
+      if (exhausted && !undispensed && !__any_sync(kFullMask, any_active)) {
+        if (kSpread) finalize_pixels();
+        break;                                                      // frame done for this warp
+      }
+      continue;                                                     // only sky / padding so far: hand out more
     }
 
     // ---------------------------------------------------------------- dense traversal of the round
@@ -676,20 +745,15 @@ __global__ void __launch_bounds__(512, 1) render_warpqueue_kernel(const __grid_c
           r.o = v3(ro.x, ro.y, ro.z);
           r.d = v3(rd.x, rd.y, rd.z);
           const float t = sphere_t(g.x, g.y, g.z, g.w, r, ro.w, 0.1f, 1000000000.0f);
-          if (t >= 0.0f) {
-            // best only ever decreases, so a (possibly stale) plain read that is already <= key proves the atomic useless
-            const unsigned long long key = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)li;
-            if (key < *reinterpret_cast<volatile unsigned long long *>(best + slot)) atomicMin(best + slot, key);
-          }
+          if (t >= 0.0f) atomicMin(best + slot, ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)li);
         }
         ltop -= n;
       } else {
-        // ---- node batch: one BVH2C node step (both children's boxes) for 32 (ray, node) pairs
+        // ---- node batch: one BVH2C node step (both children's boxes) for up to 32 (ray, node) pairs
         const int n = ntop < 32 ? ntop : 32;
-        bool pl_node = false, pr_node = false;
+        bool pl_node = false, pr_node = false, pl_leaf = false, pr_leaf = false;
         uint32_t tag = 0;
-        int lptr = 0, rptr = 0, nleaf = 0;
-        int lf0 = 0, lf1 = 0, lf2 = 0, lf3 = 0;  // up to 4 leaves reached by this item (registers, no local array)
+        int lptr = 0, rptr = 0;
         if (lane < n) {
           const uint32_t it = nstk[ntop - 1 - lane];
           tag = it & ~kIndexMask;
@@ -706,37 +770,24 @@ __global__ void __launch_bounds__(512, 1) render_warpqueue_kernel(const __grid_c
           rptr = __float_as_int(q1.w);
           const bool hl = box_hit(q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, r, q);
           const bool hr = box_hit(q2.x, q2.y, q2.z, q3.x, q3.y, q3.z, r, q);
-          pl_node = hl && lptr >= 0;
-          pr_node = hr && rptr >= 0;
-          // single leaf ~i: always visited; folded leaf pair ~(i | kPairBit): visited if its box is hit
-          const int lv = ~lptr, rv = ~rptr;
-          const bool lpair = (lv & kPairBit) != 0, rpair = (rv & kPairBit) != 0;
-          const bool ltake = lptr < 0 && (hl || !lpair), rtake = rptr < 0 && (hr || !rpair);
-          const int li0 = lv & kLeafIndexMask, ri0 = rv & kLeafIndexMask;
-          const int nl_l = ltake ? (lpair ? 2 : 1) : 0, nl_r = rtake ? (rpair ? 2 : 1) : 0;
-          nleaf = nl_l + nl_r;
-          lf0 = ltake ? li0 : ri0;
-          lf1 = nl_l == 2 ? li0 + 1 : (nl_l == 1 ? ri0 : ri0 + 1);
-          lf2 = nl_l == 2 ? ri0 : ri0 + 1;
-          lf3 = ri0 + 1;
+          pl_leaf = lptr < 0;          // a leaf child has no box in the reference: always visited
+          pr_leaf = rptr < 0;
+          pl_node = hl && !pl_leaf;
+          pr_node = hr && !pr_leaf;
         }
         __syncwarp();  // all pops have been read before anything is pushed over them
         ntop -= n;
         const unsigned bl = __ballot_sync(kFullMask, pl_node), br = __ballot_sync(kFullMask, pr_node);
+        const unsigned cl = __ballot_sync(kFullMask, pl_leaf), cr = __ballot_sync(kFullMask, pr_leaf);
         // reverse lane order: lane 0 popped the top (deepest) item, its children go back on top
         const int nb = ntop + __popc(bl & gt_mask) + __popc(br & gt_mask);
         if (pr_node) nstk[nb] = tag | (uint32_t)rptr;
         if (pl_node) nstk[nb + (pr_node ? 1 : 0)] = tag | (uint32_t)lptr;
         ntop += __popc(bl) + __popc(br);
-        // 0..4 leaf items per lane: exclusive scan from the bit planes of the count
-        const unsigned c0 = __ballot_sync(kFullMask, nleaf & 1), c1 = __ballot_sync(kFullMask, nleaf & 2),
-                       c2 = __ballot_sync(kFullMask, nleaf & 4);
-        const int lb = ltop + __popc(c0 & lt_mask) + 2 * __popc(c1 & lt_mask) + 4 * __popc(c2 & lt_mask);
-        if (nleaf > 0) lstk[lb] = tag | (uint32_t)lf0;
-        if (nleaf > 1) lstk[lb + 1] = tag | (uint32_t)lf1;
-        if (nleaf > 2) lstk[lb + 2] = tag | (uint32_t)lf2;
-        if (nleaf > 3) lstk[lb + 3] = tag | (uint32_t)lf3;
-        ltop += __popc(c0) + 2 * __popc(c1) + 4 * __popc(c2);
+        const int lb = ltop + __popc(cl & lt_mask) + __popc(cr & lt_mask);
+        if (pl_leaf) lstk[lb] = tag | (uint32_t)(~lptr);
+        if (pr_leaf) lstk[lb + (pl_leaf ? 1 : 0)] = tag | (uint32_t)(~rptr);
+        ltop += __popc(cl) + __popc(cr);
       }
       __syncwarp();
     }
@@ -746,7 +797,6 @@ __global__ void __launch_bounds__(512, 1) render_warpqueue_kernel(const __grid_c
     for (int k = 0; k < K; k++) {
       if (!((trav >> k) & 1u)) continue;
       const int slot = lane + 32 * k;
-      const int item = p_item[slot];
       const float4 ro = ray_o[slot], rd = ray_d[slot], pl = p_light[slot];
       const unsigned long long b = best[slot];
       Ray r;
@@ -761,22 +811,7 @@ __global__ void __launch_bounds__(512, 1) render_warpqueue_kernel(const __grid_c
         ray_d[slot] = make_float4(r.d.x, r.d.y, r.d.z, 0.0f);
         p_light[slot] = make_float4(light.x, light.y, light.z, __int_as_float(depth));
       } else {
-        const float4 ps = p_sum[slot];
-        int s = __float_as_int(ps.w);
-        const V3 sum = (s == 0) ? colour : vadd(v3(ps.x, ps.y, ps.z), colour);
-        s++;
-        int pi, pj;
-        item_pixel(P, item, pi, pj);
-        if (s < P.spp) {
-          const Ray nr = primary_ray(P, pi, pj, s);
-          ray_o[slot] = make_float4(nr.o.x, nr.o.y, nr.o.z, 0.0f);
-          ray_d[slot] = make_float4(nr.d.x, nr.d.y, nr.d.z, 0.0f);
-          p_light[slot] = make_float4(1.0f, 1.0f, 1.0f, __int_as_float(0));
-          p_sum[slot] = make_float4(sum.x, sum.y, sum.z, __int_as_float(s));
-        } else {
-          write_pixel(P, item, pi, pj, sum);
-          p_item[slot] = -1;
-        }
+        finish_path(slot, colour);
       }
     }
     __syncwarp();
@@ -812,14 +847,13 @@ cudaError_t configure_kernels(int max_dynamic_smem) {
   RAYB200_SET((wavefront_bounce_kernel<true, false>));
   RAYB200_SET((wavefront_bounce_kernel<false, true>));
   RAYB200_SET((wavefront_bounce_kernel<false, false>));
-  RAYB200_SET((render_warpqueue_kernel<1, true, true>));
-  RAYB200_SET((render_warpqueue_kernel<1, true, false>));
-  RAYB200_SET((render_warpqueue_kernel<1, false, true>));
-  RAYB200_SET((render_warpqueue_kernel<1, false, false>));
-  RAYB200_SET((render_warpqueue_kernel<2, true, true>));
-  RAYB200_SET((render_warpqueue_kernel<2, true, false>));
-  RAYB200_SET((render_warpqueue_kernel<2, false, true>));
-  RAYB200_SET((render_warpqueue_kernel<2, false, false>));
+#define RAYB200_SET_WQ(KK, SP)                                  \
+  RAYB200_SET((render_warpqueue_kernel<KK, SP, true, true>));   \
+  RAYB200_SET((render_warpqueue_kernel<KK, SP, true, false>));  \
+  RAYB200_SET((render_warpqueue_kernel<KK, SP, false, true>));  \
+  RAYB200_SET((render_warpqueue_kernel<KK, SP, false, false>));
+  RAYB200_SET_WQ(1, false) RAYB200_SET_WQ(1, true) RAYB200_SET_WQ(2, false) RAYB200_SET_WQ(2, true)
+#undef RAYB200_SET_WQ
 #undef RAYB200_SET
   return cudaSuccess;
 }
@@ -864,14 +898,18 @@ void launch_render(const RenderParams &p, const LaunchConfig &lc, const Wavefron
     long long ctas = lc.sm_count;
     const long long useful = (items + 32 * k * lc.wq_warps - 1) / (32 * k * lc.wq_warps);
     if (ctas > useful) ctas = useful;
-#define RAYB200_WQ(KK, A, S) render_warpqueue_kernel<KK, A, S><<<(unsigned)ctas, wthreads, wsmem, stream>>>(p, ncap)
-    if (k == 1) {
-      if (all_nodes && sph) RAYB200_WQ(1, true, true); else if (all_nodes) RAYB200_WQ(1, true, false);
-      else if (sph) RAYB200_WQ(1, false, true); else RAYB200_WQ(1, false, false);
-    } else {
-      if (all_nodes && sph) RAYB200_WQ(2, true, true); else if (all_nodes) RAYB200_WQ(2, true, false);
-      else if (sph) RAYB200_WQ(2, false, true); else RAYB200_WQ(2, false, false);
-    }
+#define RAYB200_WQ(KK, SP, A, S) render_warpqueue_kernel<KK, SP, A, S><<<(unsigned)ctas, wthreads, wsmem, stream>>>(p, ncap)
+#define RAYB200_WQ2(KK, SP)                                                               \
+  do {                                                                                    \
+    if (all_nodes && sph) RAYB200_WQ(KK, SP, true, true);                                 \
+    else if (all_nodes) RAYB200_WQ(KK, SP, true, false);                                  \
+    else if (sph) RAYB200_WQ(KK, SP, false, true);                                        \
+    else RAYB200_WQ(KK, SP, false, false);                                                \
+  } while (0)
+    const bool spread = p.sample_buf != nullptr;
+    if (k == 1) { if (spread) RAYB200_WQ2(1, true); else RAYB200_WQ2(1, false); }
+    else { if (spread) RAYB200_WQ2(2, true); else RAYB200_WQ2(2, false); }
+#undef RAYB200_WQ2
 #undef RAYB200_WQ
     (*launches)++;
     return;

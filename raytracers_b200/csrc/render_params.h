@@ -3,8 +3,6 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 
-#include "bvh_layout.h"
-
 namespace rayb200 {
 
 constexpr int kTileW = 8;       // a warp renders an 8x4-pixel tile (coherent primary rays, 128-B stores)
@@ -19,8 +17,7 @@ struct RenderParams {
   const float4 *nodes_soa;  // component-major copy (source of the shared-memory staging)
   const float4 *geom;
   const float4 *colour;
-  int32_t n_inner, n_leaves;   // n_inner = STORED nodes (leaf-pair parents are folded away, scene_host.h)
-  int32_t root_ptr;            // 0, or a leaf-pair code when the scene has exactly 2 spheres
+  int32_t n_inner, n_leaves;
   int32_t smem_nodes;    // first smem_nodes BFS nodes are staged in shared memory (persistent/wavefront kernels)
   int32_t smem_spheres;  // first smem_spheres sphere records staged (0 or n_leaves)
   int32_t max_depth;     // depth of the deepest leaf (root = 0): bounds the traversal stacks
@@ -36,6 +33,7 @@ struct RenderParams {
   // sharding: this rank renders tiles t = lt * world + rank
   int32_t rank, world, tiles_x, tiles_y;
   int64_t n_tiles, local_tiles;
+  float4 *sample_buf;    // warp-queue kernel, spp > 1: [CTAs][warps][kWqRing][spp] finished-sample colours (else NULL)
   // persistent-threads work cursor and optional work counters
   int32_t *work_cursor;
   unsigned long long *counters;  // [4] segments, node_steps, box_tests, leaf_tests (counting kernels only)
@@ -74,11 +72,13 @@ void launch_detile(const int32_t *gathered, int32_t *out, int64_t H, int64_t W, 
 __host__ __device__ inline size_t staging_bytes(const RenderParams &p) {
   return 128 + (size_t)p.smem_nodes * 64 + (size_t)p.smem_spheres * 16;
 }
+constexpr int kWqRing = 8;         // warp-queue kernel: pixels a warp may have open at once when samples are spread
+constexpr int kWqLeafStack = 128;  // warp-queue kernel: leaf-item stack (never more than 31 + 64 live)
 // warp-queue kernel: node-stack capacity (proved bound, see render_kernels.cu) and per-warp / per-CTA bytes
 __host__ __device__ inline int wq_node_capacity(int k, int max_depth) { return 32 * k + 64 * (max_depth + 1); }
 __host__ __device__ inline size_t wq_warp_bytes(int k, int ncap) {
   const size_t r = 32 * (size_t)k;
-  return ((r * (16 * 5 + 8 + 4) + 128 * 4 + (size_t)ncap * 4) + 127) & ~(size_t)127;
+  return ((r * (16 * 5 + 8 + 4) + 2 * kWqRing * 4 + kWqLeafStack * 4 + (size_t)ncap * 4) + 127) & ~(size_t)127;
 }
 cudaError_t configure_kernels(int max_dynamic_smem);
 

@@ -170,8 +170,8 @@ bool build_lbvh(const HostScene &s, Lbvh &t, std::string *err) {
     if (err) *err = "prepare_scene: a scene needs at least 2 spheres (the reference indexes I[0], bvh.fut:65)";
     return false;
   }
-  if (n > (int64_t)1 << 26) {
-    if (err) *err = "prepare_scene: too many spheres (this build packs leaf indices into 26 bits)";
+  if (n > (int64_t)1 << 30) {
+    if (err) *err = "prepare_scene: too many spheres (i32 indices, radixtree.fut:24)";
     return false;
   }
   t.n = n;
@@ -311,48 +311,41 @@ bool build_lbvh(const HostScene &s, Lbvh &t, std::string *err) {
 void pack_bvh(const HostScene &s, const Lbvh &t, PackedBvh &out) {
   const int64_t n = t.n;
   const int32_t ni = (int32_t)(n - 1);
-  auto is_pair = [&](int32_t k) { return t.left[(size_t)k] < 0 && t.right[(size_t)k] < 0; };
-  auto pair_code = [&](int32_t k) { return ~((~t.left[(size_t)k]) | kPairBit); };  // leaves (i, i+1), i = ~left
-  // BFS order over the stored nodes: the first K packed nodes are the top of the tree (what the kernels
-  // stage in shared memory).  Leaf-pair parents are folded into their parent's child pointer.
+  // BFS order: the first K packed nodes are the top of the tree (what the kernels stage in shared memory)
   std::vector<int32_t> order, newidx((size_t)ni, -1);
   order.reserve((size_t)ni);
-  if (!is_pair(0)) order.push_back(0);
+  order.push_back(0);
   for (size_t head = 0; head < order.size(); head++) {
     const int32_t k = order[head];
     newidx[(size_t)k] = (int32_t)head;
-    const int32_t ch[2] = {t.left[(size_t)k], t.right[(size_t)k]};
-    for (int c = 0; c < 2; c++)
-      if (ch[c] >= 0 && !is_pair(ch[c])) order.push_back(ch[c]);
+    if (t.left[(size_t)k] >= 0) order.push_back(t.left[(size_t)k]);
+    if (t.right[(size_t)k] >= 0) order.push_back(t.right[(size_t)k]);
   }
-  out.root_ptr = is_pair(0) ? pair_code(0) : 0;
-  const size_t stored = order.size();
-  out.nodes.resize(stored * 4);
+  out.nodes.resize((size_t)ni * 4);
   const float inf = std::numeric_limits<float>::infinity();
   auto as_float = [](int32_t v) { float f; std::memcpy(&f, &v, 4); return f; };
-  par_for((int64_t)stored, [&](int64_t pos) {
+  par_for(ni, [&](int64_t pos) {
     const int32_t k = order[(size_t)pos];
     F4 *q = &out.nodes[(size_t)pos * 4];
     const int32_t ch[2] = {t.left[(size_t)k], t.right[(size_t)k]};
-    int32_t ptr[2];
     for (int c = 0; c < 2; c++) {
       float b[6];
-      if (ch[c] < 0) {  // single leaf: no box in the reference -> always-pass box
+      int32_t ptr;
+      if (ch[c] < 0) {
         b[0] = b[1] = b[2] = -inf; b[3] = b[4] = b[5] = inf;
-        ptr[c] = ch[c];
+        ptr = ch[c];
       } else {
         std::memcpy(b, &t.boxes[(size_t)ch[c] * 6], sizeof b);
-        ptr[c] = is_pair(ch[c]) ? pair_code(ch[c]) : newidx[(size_t)ch[c]];
+        ptr = newidx[(size_t)ch[c]];
       }
-      q[2 * c + 0] = F4{b[0], b[1], b[2], 0.0f};
+      q[2 * c + 0] = F4{b[0], b[1], b[2], c == 0 ? as_float(ptr) : 0.0f};
       q[2 * c + 1] = F4{b[3], b[4], b[5], 0.0f};
+      if (c == 1) q[1].w = as_float(ptr);
     }
-    q[0].w = as_float(ptr[0]);
-    q[1].w = as_float(ptr[1]);
   });
-  out.nodes_soa.resize(stored * 4);
-  par_for((int64_t)stored, [&](int64_t pos) {
-    for (int c = 0; c < 4; c++) out.nodes_soa[(size_t)c * stored + (size_t)pos] = out.nodes[(size_t)pos * 4 + c];
+  out.nodes_soa.resize((size_t)ni * 4);
+  par_for(ni, [&](int64_t pos) {
+    for (int c = 0; c < 4; c++) out.nodes_soa[(size_t)c * ni + (size_t)pos] = out.nodes[(size_t)pos * 4 + c];
   });
   out.geom.resize((size_t)n);
   out.colour.resize((size_t)n);

@@ -4,8 +4,6 @@
 #pragma once
 #include <cstdint>
 #include <string>
-
-#include "bvh_layout.h"
 #include <vector>
 
 namespace rayb200 {
@@ -44,17 +42,12 @@ struct Lbvh {
 //   q2 = {Rmin.x, Rmin.y, Rmin.z, 0}            q3 = {Rmax.x, Rmax.y, Rmax.z, 0}
 // A child that is a leaf has no box in the reference (bvh.fut:84 applies `op` without `contains`);
 // it is stored as [-inf, +inf]^3, which passes aabb_hit for every ray, so the node step is uniform.
-// Inner nodes whose two children are both leaves (37-46 % of all inner nodes) are not stored at all:
-// the walk does nothing there except visit both leaves, and in a Karras tree those leaves are
-// consecutive (i, i+1), so their parent is encoded in ITS parent's child pointer as a "leaf pair"
-// that keeps the eliminated node's box.
-// Child pointers: inner -> packed BFS index (>= 0); single leaf i -> ~i; leaf pair (i, i+1) -> ~(i | kPairBit).
+// Child pointers: inner -> BFS index (>= 0), leaf i -> ~i (Morton-sorted leaf index, < 0).
 struct PackedBvh {
-  std::vector<F4> nodes;    // 4 * (number of stored nodes), node-major (one 64-B record per node: global/L2 fetches)
+  std::vector<F4> nodes;    // 4 * (n-1), node-major (one 64-B record per node: global/L2 fetches)
   std::vector<F4> nodes_soa;  // the same records component-major: [q0 of all][q1 of all][q2][q3] — the copy that
                               // is staged into shared memory, where a 16-B stride spreads random node indices
                               // over all bank groups (the 64-B stride of `nodes` would hit only 2 of 8)
-  int32_t root_ptr = 0;     // 0 (stored root) or a leaf-pair code when n == 2
   std::vector<F4> geom;     // n x {centre.xyz, radius}, Morton-sorted order (= bvh.L)
   std::vector<F4> colour;   // n x {r, g, b, 0}
   float root_box[6];        // the root's own box (tested once per segment)

@@ -93,6 +93,41 @@ def test_spp_extension_vs_oracle(R, oracle, name, spp, kernel):
     np.testing.assert_array_equal(rgb.view(np.uint32), want_rgb.view(np.uint32))  # ... and in fact bit-exact
 
 
+@pytest.mark.parametrize("tuning", [dict(wq_spread=1, wq_warps=16, wq_k=1), dict(wq_spread=1, wq_warps=3, wq_k=2),
+                                    dict(wq_spread=0, wq_warps=8, wq_k=2), dict(wq_spread=1, wq_warps=24, wq_k=1)])
+def test_warpqueue_sample_spreading(R, oracle, tuning):
+    """spp > 1 on the warp-queue kernel: samples of a pixel are traced by different lanes and summed in
+    sample order afterwards — must be bit-identical to the sequential definition, also on partial tiles
+    and in the compact (sharded) output layout."""
+    import torch
+    from raytracers_b200 import distributed as D
+    h, w, spp = 45, 83, 5
+    want, want_rgb, _ = oracle.Scene.rgbbox().prepare(h, w).render(h, w, spp=spp, want_rgb=True)
+    with R.Context(kernel="warpqueue", **tuning) as ctx:
+        pr = ctx.prepare_scene(h, w, ctx.rgbbox())
+        pix, rgb = ctx.render_host(h, w, pr, spp=spp, want_rgb=True)
+        assert_same(pix, want, f"warpqueue spread {tuning}")
+        np.testing.assert_array_equal(rgb.view(np.uint32), want_rgb.view(np.uint32))
+        world = 3
+        padded = D.tile_layout(h, w, world)[3]
+        for rank in range(world):
+            tiles = torch.empty((padded, 32), dtype=torch.int32, device="cuda")
+            ctx.set_shard(rank, world)
+            ctx.render_shard_into(tiles.data_ptr(), h, w, pr, spp=spp)
+            ctx.sync()
+            np.testing.assert_array_equal(tiles.cpu().numpy(), D.extract_rank_tiles(want, rank, world))
+
+
+def test_headline_config_64spp_kernels_agree(R):
+    """BASELINE configs[1]/[2] (1000x1000, 64 spp): too slow for the CPU oracle inside a test, so the kernels
+    (lane-bound K1, sample-spread K3, pixel-bound K3) are checked against each other bit-for-bit."""
+    for name in ("rgbbox", "irreg"):
+        a = gpu_frame(R, name, 1000, 1000, "persistent", spp=64)
+        b = gpu_frame(R, name, 1000, 1000, "warpqueue", spp=64)
+        c = gpu_frame(R, name, 1000, 1000, "warpqueue", spp=64, wq_spread=0)
+        assert sha(a) == sha(b) == sha(c), name
+
+
 def test_custom_scenes_edge_cases(R, oracle):
     cam = np.float32([0, 0, 20, 0, 0, 0, 60])
     cases = {
