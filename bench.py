@@ -313,6 +313,33 @@ def run_ours(args):
             ms.sort()
             one_spp[name] = round(ms[len(ms) // 2], 4)
 
+    extra = None
+    if rank == 0 and world == 1 and args.extra:
+        extra = {}
+        peak, _ = measured_peak_gbs()
+        for tag, scene_args, hh, ww, spp in (("irreg_4000x4000_1spp", ("irreg",), 4000, 4000, 1),
+                                             ("irreg_4000x4000_256spp", ("irreg",), 4000, 4000, 256),
+                                             ("random1M_2000x2000_16spp", ("random", 1000000, 1), 2000, 2000, 16)):
+            t0 = time.perf_counter()
+            sc = ctx.scene(scene_args[0], n=scene_args[1] if len(scene_args) > 1 else None)
+            pr = ctx.prepare_scene(hh, ww, sc)
+            ctx.sync()
+            prep_s = time.perf_counter() - t0
+            wk = ctx.count_work(hh, ww, pr, spp=spp)
+            fr = torch.empty((hh, ww), dtype=torch.int32, device="cuda")
+            ms = []
+            for _ in range(3 if spp * hh * ww < 2e9 else 2):
+                ctx.render_into(fr.data_ptr(), hh, ww, pr, spp=spp)
+                torch.cuda.synchronize()
+                ms.append(ctx.last_render_ms())
+            m = sorted(ms)[len(ms) // 2]
+            gb = (32 * wk["box_tests"] + 16 * wk["leaf_tests"] + 4 * hh * ww) / 1e9
+            extra[tag] = {"ms_per_frame": round(m, 3), "segments": wk["segments"], "Mrays_s": round(wk["segments"] / m / 1e3, 1),
+                          "algorithmic_GB": round(gb, 2), "GB_s": round(gb / m * 1e3, 1), "roofline_frac": round(gb / m * 1e3 / peak, 4),
+                          "prepare_scene_s": round(prep_s, 3), "info": {k: (int(v) if not hasattr(v, "shape") else None) for k, v in pr.info().items() if k in ("n_leaves", "max_depth", "smem_nodes", "stale_nodes")}}
+            del fr
+            pr.free(); sc.free()
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         segs, secs, cores = cpu_sample()
@@ -329,7 +356,7 @@ def run_ours(args):
                        "parallelism": f"tile-sharded x{world}, one NCCL gather per frame" if world > 1 else "single GPU",
                        "ray": "one ray segment = one objs_hit call (ray.fut:76-86)"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-            "frame_ms_1spp": one_spp,
+            "frame_ms_1spp": one_spp, "extra": extra,
             "published_reference_1spp_ms": {"futhark_multicore_ryzen1700x": {"rgbbox": 179, "irreg": 62},
                                             "futhark_gpu_mi100": {"rgbbox": 14, "irreg": 8}},
         }
@@ -348,6 +375,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--kernel", default=os.environ.get("RAY_KERNEL", "auto"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--extra", action="store_true",
+                    help="also measure (once, outside the timed steps) BASELINE configs[3] and [4]: irreg 4000x4000 256spp and the 1M-sphere scene")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -26,7 +26,7 @@ struct futhark_context_config {
   int32_t kernel = RAY_B200_KERNEL_AUTO;
   int32_t rank = 0, world = 1;
   int32_t block_threads = 256, blocks_per_sm = 4, smem_budget = 48 * 1024, refill_min = 8, tail_from = 8;
-  int32_t wq_warps = 16, wq_k = 1, wq_spread = 1;
+  int32_t wq_warps = 24, wq_k = 1, wq_spread = 1, permute = 1;
   std::string cache_file;
 };
 
@@ -45,6 +45,7 @@ struct futhark_context {
   int32_t offsets_spp = 0;
   int64_t launches = 0;
   WavefrontBuffers wf;                      // ray queues of the wavefront kernel (grown on demand)
+  int32_t plan_wq_warps = 0;                // warps per CTA the warp-queue kernel will use for the frame being set up
   float4 *sample_buf = nullptr;             // warp-queue kernel, spp > 1: per-warp finished-sample colours
   size_t sample_buf_bytes = 0;
   bool profiling_paused = false;
@@ -115,7 +116,7 @@ int parse_kernel(const char *v, int dflt) {
   return atoi(v);
 }
 
-const char *kTuningNames[] = {"kernel", "spp", "blocks_per_sm", "smem_budget", "refill_min", "tail_from", "wq_warps", "wq_k", "wq_spread", "rank", "world"};
+const char *kTuningNames[] = {"kernel", "spp", "blocks_per_sm", "smem_budget", "refill_min", "tail_from", "wq_warps", "wq_k", "wq_spread", "permute", "rank", "world"};
 constexpr int kNumTuning = sizeof(kTuningNames) / sizeof(kTuningNames[0]);
 
 bool bad_ctx(futhark_context *ctx) { return ctx == nullptr || !ctx->ok; }
@@ -164,17 +165,30 @@ int fill_params(futhark_context *ctx, const futhark_opaque_prepared_scene *p, in
   P.tiles_x = (int32_t)((w + kTileW - 1) / kTileW); P.tiles_y = (int32_t)((h + kTileH - 1) / kTileH);
   P.n_tiles = tiles_total(h, w);
   P.local_tiles = tiles_of_rank(h, w, rank, world);
+  P.n_chunks = (int32_t)((P.local_tiles + 63) / 64);
+  {  // stride ~ golden ratio * n_chunks, made coprime to n_chunks
+    auto gcd = [](int64_t a, int64_t b) { while (b) { const int64_t t = a % b; a = b; b = t; } return a; };
+    int64_t st = std::max<int64_t>(1, (int64_t)(0.6180339887 * (double)P.n_chunks));
+    while (gcd(st, P.n_chunks) != 1) st++;
+    P.chunk_stride = (int32_t)(P.n_chunks > 1 ? st % P.n_chunks : 0);
+    if (P.n_chunks > 1 && P.chunk_stride == 0) P.chunk_stride = 1;
+    if (!ctx->cfg.permute) { P.chunk_stride = 1; }
+  }
   P.work_cursor = ctx->work_cursor;
   P.counters = ctx->counters;
   // shared-memory staging plan: BFS prefix of the node array, then the sphere records if they all fit.
   // The warp-queue kernel runs one CTA per SM and gives the staging area whatever its queues leave.
   int64_t budget = std::min<int64_t>(ctx->cfg.smem_budget, ctx->max_smem_optin - 1024) - 128;
   if (resolve_kernel(ctx) == RAY_B200_KERNEL_WARPQUEUE) {
+    // one CTA per SM: as many warps as asked for (<= 24) while their queues leave >= 8 KB for staging;
+    // deep trees need bigger node stacks, so they get fewer warps
     const int k = ctx->cfg.wq_k == 1 ? 1 : 2;
-    const int64_t wq_w = ctx->cfg.wq_warps < 1 ? 1 : (ctx->cfg.wq_warps > 24 ? 24 : ctx->cfg.wq_warps);
-    const int64_t queues = wq_w * (int64_t)wq_warp_bytes(k, wq_node_capacity(k, p->max_depth));
-    budget = (int64_t)ctx->max_smem_optin - queues - 512;
-    if (budget < 0) { set_error(ctx, "render: warp-queue kernel does not fit shared memory (depth %d, %d warps)", p->max_depth, ctx->cfg.wq_warps); return 1; }
+    const int64_t per_warp = (int64_t)wq_warp_bytes(k, wq_node_capacity(k, p->max_depth));
+    int64_t wq_w = ctx->cfg.wq_warps < 1 ? 1 : (ctx->cfg.wq_warps > 24 ? 24 : ctx->cfg.wq_warps);
+    while (wq_w > 1 && wq_w * per_warp + 8192 > (int64_t)ctx->max_smem_optin) wq_w--;
+    budget = (int64_t)ctx->max_smem_optin - wq_w * per_warp - 512;
+    if (budget < 256) { set_error(ctx, "render: warp-queue kernel does not fit shared memory (tree depth %d)", p->max_depth); return 1; }
+    ctx->plan_wq_warps = (int32_t)wq_w;
   }
   int64_t nodes_fit = std::max<int64_t>(0, budget / 64);
   P.smem_nodes = (int32_t)std::min<int64_t>(P.n_inner, nodes_fit);
@@ -185,7 +199,7 @@ int fill_params(futhark_context *ctx, const futhark_opaque_prepared_scene *p, in
 
 int resolve_kernel(const futhark_context *ctx) {
   int k = ctx->cfg.kernel;
-  if (k == RAY_B200_KERNEL_AUTO) k = RAY_B200_KERNEL_PERSISTENT;
+  if (k == RAY_B200_KERNEL_AUTO) k = RAY_B200_KERNEL_WARPQUEUE;  // fastest measured variant on every BASELINE config
   return k;
 }
 
@@ -231,7 +245,7 @@ int do_render(futhark_context *ctx, RenderParams &P) {
   lc.smem_budget = ctx->cfg.smem_budget;
   lc.refill_min = ctx->cfg.refill_min;
   lc.tail_from = ctx->cfg.tail_from;
-  lc.wq_warps = ctx->cfg.wq_warps < 1 ? 1 : (ctx->cfg.wq_warps > 24 ? 24 : ctx->cfg.wq_warps);
+  lc.wq_warps = ctx->plan_wq_warps > 0 ? ctx->plan_wq_warps : 1;
   lc.wq_k = ctx->cfg.wq_k == 1 ? 1 : 2;
   if (lc.kernel == RAY_B200_KERNEL_WAVEFRONT && ensure_wavefront(ctx, P.local_tiles * kTilePixels)) return 1;
   P.sample_buf = nullptr;
@@ -334,6 +348,7 @@ int futhark_context_config_set_tuning_param(struct futhark_context_config *cfg, 
   else if (!strcmp(name, "wq_warps")) cfg->wq_warps = (int32_t)v;
   else if (!strcmp(name, "wq_k")) cfg->wq_k = (int32_t)v;
   else if (!strcmp(name, "wq_spread")) cfg->wq_spread = (int32_t)v;
+  else if (!strcmp(name, "permute")) cfg->permute = (int32_t)v;
   else if (!strcmp(name, "rank")) cfg->rank = (int32_t)v;
   else if (!strcmp(name, "world")) cfg->world = (int32_t)v;
   else return 1;
@@ -357,6 +372,7 @@ struct futhark_context *futhark_context_new(struct futhark_context_config *cfg) 
   ctx->cfg.wq_warps = env_int("RAY_WQ_WARPS", ctx->cfg.wq_warps);
   ctx->cfg.wq_k = env_int("RAY_WQ_K", ctx->cfg.wq_k);
   ctx->cfg.wq_spread = env_int("RAY_WQ_SPREAD", ctx->cfg.wq_spread);
+  ctx->cfg.permute = env_int("RAY_PERMUTE", ctx->cfg.permute);
   memset(&ctx->wf, 0, sizeof ctx->wf);
 
   auto fail = [&](const char *what, cudaError_t e) {

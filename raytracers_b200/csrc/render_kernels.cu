@@ -198,6 +198,13 @@ __device__ __forceinline__ bool item_pixel(const RenderParams &P, int k, int &i,
   return t < P.n_tiles && i < P.W && j < P.H;
 }
 
+// claim index (value of the global work cursor) -> item index: chunks of 64 tiles in stride-permuted order
+__device__ __forceinline__ int claim_to_item(const RenderParams &P, int c) {
+  const int chunk = c >> 11;
+  const int perm = (int)(((long long)chunk * P.chunk_stride) % P.n_chunks);
+  return (perm << 11) | (c & 2047);
+}
+
 __device__ __forceinline__ void write_pixel(const RenderParams &P, int k, int i, int j, V3 sum) {
   const V3 col = (P.spp == 1) ? sum : vscale(P.inv_spp, sum);
   const int pix = pack_pixel(col);
@@ -329,8 +336,8 @@ __global__ void __launch_bounds__(256, 2) render_persistent_kernel(const __grid_
 
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
-  const long long total64 = P.local_tiles * kTilePixels;
-  const int total = (int)total64;
+  const int total = (int)(P.local_tiles * kTilePixels);
+  const int total_claims = P.n_chunks << 11;
   WorkCounters wc;
 
   int item = -1, pi = 0, pj = 0, s = 0, depth = 0;
@@ -348,7 +355,8 @@ __global__ void __launch_bounds__(256, 2) render_persistent_kernel(const __grid_
       if (lane == leader) base = atomicAdd(P.work_cursor, cnt);
       base = __shfl_sync(kFullMask, base, leader);
       if (item < 0) {
-        const int k = base + __popc(idle & lt_mask);
+        const int c = base + __popc(idle & lt_mask);
+        const int k = c < total_claims ? claim_to_item(P, c) : total;
         if (k < total) {
           if (item_pixel(P, k, pi, pj)) {
             item = k;
@@ -361,7 +369,7 @@ __global__ void __launch_bounds__(256, 2) render_persistent_kernel(const __grid_
           }
         }
       }
-      exhausted = base + cnt >= total;
+      exhausted = base + cnt >= total_claims;
       idle = __ballot_sync(kFullMask, item < 0);
     }
     if (idle == kFullMask) {
@@ -530,6 +538,7 @@ __global__ void __launch_bounds__(768, 1) render_warpqueue_kernel(const __grid_c
   uint32_t *nstk = lstk + kWqLeafStack;
 
   const int total = (int)(P.local_tiles * kTilePixels);
+  const int total_claims = P.n_chunks << 11;
   const int spp = P.spp;
 #pragma unroll
   for (int k = 0; k < K; k++) p_item[lane + 32 * k] = -1;
@@ -616,7 +625,8 @@ __global__ void __launch_bounds__(768, 1) render_warpqueue_kernel(const __grid_c
           for (int k = 0; k < K; k++) {
             const int slot = lane + 32 * k;
             if (p_item[slot] < 0) {
-              const int item = base + rank++;
+              const int c = base + rank++;
+              const int item = c < total_claims ? claim_to_item(P, c) : total;
               int pi, pj;
               if (item < total) {
                 if (item_pixel(P, item, pi, pj)) {
@@ -632,17 +642,20 @@ __global__ void __launch_bounds__(768, 1) render_warpqueue_kernel(const __grid_c
               }
             }
           }
-          exhausted = base + cnt >= total;
+          exhausted = base + cnt >= total_claims;
         }
       } else if (cnt) {
         int avail = (open_seq - disp_seq) * spp - disp_s;
         while (!exhausted && avail < cnt) {  // open more pixels (one cursor claim each) while the ring has room
           const int m = open_seq & (kWqRing - 1);
           if (ring_done[m] != -1) break;
-          int item = 0;
-          if (lane == 0) item = atomicAdd(P.work_cursor, 1);
-          item = __shfl_sync(kFullMask, item, 0);
-          if (item >= total) { exhausted = true; break; }
+          int c = 0;
+          if (lane == 0) c = atomicAdd(P.work_cursor, 1);
+          c = __shfl_sync(kFullMask, c, 0);
+          if (c >= total_claims) { exhausted = true; break; }
+          const int item = claim_to_item(P, c);
+          if (item >= total) continue;  // tail of the last (partial) chunk
+          __syncwarp();                 // every lane has read ring_done[m] before lane 0 overwrites it
           if (lane == 0) { ring_item[m] = item; ring_done[m] = 0; }
           __syncwarp();
           open_seq++;

@@ -33,6 +33,10 @@ struct RenderParams {
   // sharding: this rank renders tiles t = lt * world + rank
   int32_t rank, world, tiles_x, tiles_y;
   int64_t n_tiles, local_tiles;
+  // claim order of the persistent kernels: work is claimed in chunks of 64 tiles (2048 pixels) and the
+  // chunk order is a stride permutation (chunk * chunk_stride mod n_chunks, stride coprime to n_chunks), so
+  // the cheap sky and the 50-bounce ground of a frame are interleaved instead of the heavy rows coming last
+  int32_t n_chunks, chunk_stride;
   float4 *sample_buf;    // warp-queue kernel, spp > 1: [CTAs][warps][kWqRing][spp] finished-sample colours (else NULL)
   // persistent-threads work cursor and optional work counters
   int32_t *work_cursor;

@@ -51,7 +51,8 @@ def main():
     ap.add_argument("--smem_budget", default="65536")
     ap.add_argument("--tail_from", default="8")
     ap.add_argument("--wq_warps", default="16")
-    ap.add_argument("--wq_k", default="2")
+    ap.add_argument("--wq_k", default="1")
+    ap.add_argument("--permute", default="1")
     a = ap.parse_args()
     rows = []
     for cfg in a.configs.split(","):
@@ -65,7 +66,7 @@ def main():
             elif kernel == "wavefront":
                 grid = itertools.product(a.blocks_per_sm.split(","), a.tail_from.split(","), a.smem_budget.split(","))
             elif kernel == "warpqueue":
-                grid = itertools.product(a.wq_warps.split(","), a.wq_k.split(","), ["x"])
+                grid = itertools.product(a.wq_warps.split(","), a.wq_k.split(","), a.permute.split(","))
             else:
                 grid = itertools.product(a.blocks_per_sm.split(","), a.refill_min.split(","), a.smem_budget.split(","))
             for bps, rf, sb in grid:
@@ -74,11 +75,15 @@ def main():
                 elif kernel == "wavefront":
                     tuning = dict(blocks_per_sm=int(bps), tail_from=int(rf), smem_budget=int(sb))
                 elif kernel == "warpqueue":
-                    tuning = dict(wq_warps=int(bps), wq_k=int(rf))
+                    tuning = dict(wq_warps=int(bps), wq_k=int(rf), permute=int(sb))
                 else:
                     tuning = dict(blocks_per_sm=int(bps), refill_min=int(rf), smem_budget=int(sb))
                 t0 = time.time()
-                med, best, hsh = run(name, h, w, spp, kernel, a.reps, n=n, **tuning)
+                try:
+                    med, best, hsh = run(name, h, w, spp, kernel, a.reps, n=n, **tuning)
+                except R.RayError as e:
+                    print(json.dumps(dict(config=cfg, kernel=kernel, **tuning, error=str(e))), flush=True)
+                    continue
                 ref_hash = ref_hash or hsh
                 row = dict(config=cfg, kernel=kernel, **tuning, ms_median=round(med, 4), ms_best=round(best, 4), hash=hsh,
                            same_as_first=(hsh == ref_hash), wall=round(time.time() - t0, 2))
