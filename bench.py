@@ -38,6 +38,31 @@ METRIC = "Mrays/s (ray segments/s) rgbbox+irreg 1000x1000"
 WORKLOAD = "rgbbox 1000x1000 64spp + irreg 1000x1000 64spp per step (BASELINE.json configs[1]+configs[2])"
 
 
+def dram_traffic_per_launch():
+    """dram__bytes_read.sum + dram__bytes_write.sum per render launch from the committed ncu capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "dram_traffic.json")) as f:
+            d = json.load(f)
+        return {k: int(d[k]) for k in SCENES}
+    except Exception:
+        return None
+
+
+def host_cpu_quota():
+    """CPUs this container may actually use (cgroup v2 cpu.max), or None when unlimited/unknown."""
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        return None if quota == "max" else round(int(quota) / int(period), 2)
+    except Exception:
+        pass
+    try:  # cgroup v1
+        quota = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+        period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+        return None if quota <= 0 else round(quota / period, 2)
+    except Exception:
+        return None
+
+
 def measured_peak_gbs():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -142,7 +167,8 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * wall / args.steps, 3),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": sample, "host": "cpu"},
-        "cpu_baseline": {"value": round(value, 3), "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": round(value, 3), "unit": "Mrays/s", "cores": cores, "cgroup_cpu_quota": host_cpu_quota(),
+                         "kind": "port", "sample": sample},
         "e2e": {"value": round(value, 3), "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -251,8 +277,10 @@ def run_ours(args):
         tot_bytes = sum(alg_bytes.values())
         tot_ms = sum(per_scene[n]["ms_per_frame"] for n in SCENES)
         ach = tot_bytes / tot_ms / 1e6
+        traffic = dram_traffic_per_launch()
         roof = {"bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
-                "traffic": None, "peak_source": how, "kernel": f"render ({args.kernel}) — one launch per frame",
+                "traffic": (sum(traffic.values()) / len(traffic) if traffic else None), "traffic_per_scene": traffic,
+                "traffic_source": "profiles/dram_traffic.json (ncu --set full, per launch)", "peak_source": how, "kernel": f"render ({args.kernel}) — one launch per frame",
                 "algorithmic_bytes_per_launch": {n: alg_bytes[n] for n in SCENES}, "per_scene": per_scene,
                 "note": "algorithmic bytes = 32 B x box tests + 16 B x sphere tests of the REFERENCE traversal + 4 B x pixels; "
                         "the scene (<1 MB) is shared-memory/L2 resident, so real DRAM traffic is far below this (see profiles/)"}
@@ -343,7 +371,7 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         segs, secs, cores = cpu_sample()
-        cpu = {"value": round(segs / secs / 1e6, 3), "unit": "Mrays/s", "cores": cores, "kind": "port",
+        cpu = {"value": round(segs / secs / 1e6, 3), "unit": "Mrays/s", "cores": cores, "cgroup_cpu_quota": host_cpu_quota(), "kind": "port",
                "sample": f"rows j%{ROW_STEP}==0 of both 1000x1000 frames at {SPP} spp (1/{ROW_STEP} of a step), {secs:.1f} s"}
 
     if rank == 0:

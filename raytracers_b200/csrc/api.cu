@@ -45,6 +45,8 @@ struct futhark_context {
   int32_t offsets_spp = 0;
   int64_t launches = 0;
   WavefrontBuffers wf;                      // ray queues of the wavefront kernel (grown on demand)
+  struct PinnedBlock { unsigned char *ptr; size_t bytes; cudaEvent_t last_use; };
+  std::vector<PinnedBlock> pinned_cache;    // page-locked upload buffers of freed prepared scenes, reused by the next prepare_scene
   int32_t plan_wq_warps = 0;                // warps per CTA the warp-queue kernel will use for the frame being set up
   float4 *sample_buf = nullptr;             // warp-queue kernel, spp > 1: per-warp finished-sample colours
   size_t sample_buf_bytes = 0;
@@ -65,8 +67,11 @@ struct futhark_opaque_prepared_scene {
   CameraRec cam;
   float root_box[6];
   int32_t max_depth = 0;
+  unsigned char *d_block = nullptr; // one stream-ordered device allocation holding the four arrays below
   float4 *d_nodes = nullptr, *d_nodes_soa = nullptr, *d_geom = nullptr, *d_colour = nullptr;
   unsigned char *pinned = nullptr;  // packed nodes | nodes_soa | geom | colour in page-locked host memory (upload source)
+  size_t pinned_bytes = 0;
+  cudaEvent_t pinned_event = nullptr;  // completion of the last H2D copy that read `pinned`
   size_t nodes_bytes = 0, geom_bytes = 0, colour_bytes = 0;
   int64_t n = 0;
 };
@@ -272,26 +277,25 @@ int do_render(futhark_context *ctx, RenderParams &P) {
   return 0;
 }
 
-void free_prepared_device(futhark_opaque_prepared_scene *p) {
-  if (p->d_nodes) cudaFree(p->d_nodes);
-  if (p->d_nodes_soa) cudaFree(p->d_nodes_soa);
-  if (p->d_geom) cudaFree(p->d_geom);
-  if (p->d_colour) cudaFree(p->d_colour);
-  if (p->pinned) cudaFreeHost(p->pinned);
+// Device memory goes back to the stream-ordered pool (ordered after any render still using it);
+// the page-locked upload buffer goes to the context's cache together with the event that guards it.
+void free_prepared_device(futhark_context *ctx, futhark_opaque_prepared_scene *p) {
+  if (p->d_block) cudaFreeAsync(p->d_block, ctx->stream);
+  if (p->pinned) {
+    if (ctx->pinned_cache.size() < 4) ctx->pinned_cache.push_back({p->pinned, p->pinned_bytes, p->pinned_event});
+    else { cudaEventSynchronize(p->pinned_event); cudaEventDestroy(p->pinned_event); cudaFreeHost(p->pinned); }
+  }
+  p->d_block = nullptr;
   p->d_nodes = p->d_nodes_soa = p->d_geom = p->d_colour = nullptr;
   p->pinned = nullptr;
+  p->pinned_event = nullptr;
 }
 
 // Host -> device copy of the packed scene from page-locked memory (asynchronous on the context stream).
 int copy_prepared_h2d(futhark_context *ctx, futhark_opaque_prepared_scene *p) {
-  const unsigned char *src = p->pinned;
-  CUDA_TRY(ctx, cudaMemcpyAsync(p->d_nodes, src, p->nodes_bytes, cudaMemcpyHostToDevice, ctx->stream));
-  src += p->nodes_bytes;
-  CUDA_TRY(ctx, cudaMemcpyAsync(p->d_nodes_soa, src, p->nodes_bytes, cudaMemcpyHostToDevice, ctx->stream));
-  src += p->nodes_bytes;
-  CUDA_TRY(ctx, cudaMemcpyAsync(p->d_geom, src, p->geom_bytes, cudaMemcpyHostToDevice, ctx->stream));
-  src += p->geom_bytes;
-  CUDA_TRY(ctx, cudaMemcpyAsync(p->d_colour, src, p->colour_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  const size_t total = 2 * p->nodes_bytes + p->geom_bytes + p->colour_bytes;
+  CUDA_TRY(ctx, cudaMemcpyAsync(p->d_block, p->pinned, total, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaEventRecord(p->pinned_event, ctx->stream));
   return 0;
 }
 
@@ -304,15 +308,31 @@ int upload_prepared(futhark_context *ctx, futhark_opaque_prepared_scene *p) {
   p->nodes_bytes = pk.nodes.size() * sizeof(F4);
   p->geom_bytes = pk.geom.size() * sizeof(F4);
   p->colour_bytes = pk.colour.size() * sizeof(F4);
-  CUDA_TRY(ctx, cudaMallocHost(&p->pinned, 2 * p->nodes_bytes + p->geom_bytes + p->colour_bytes + 64));
+  const size_t total = 2 * p->nodes_bytes + p->geom_bytes + p->colour_bytes;  // every part is a multiple of 16 B
+  // page-locked staging: reuse a cached block (main.c frees and re-prepares the same scene every run)
+  for (size_t k = 0; k < ctx->pinned_cache.size(); k++) {
+    auto &b = ctx->pinned_cache[k];
+    if (b.bytes >= total && b.bytes <= 2 * total + 4096) {
+      CUDA_TRY(ctx, cudaEventSynchronize(b.last_use));  // the copy that last read this block has finished
+      p->pinned = b.ptr; p->pinned_bytes = b.bytes; p->pinned_event = b.last_use;
+      ctx->pinned_cache.erase(ctx->pinned_cache.begin() + (long)k);
+      break;
+    }
+  }
+  if (!p->pinned) {
+    CUDA_TRY(ctx, cudaMallocHost(&p->pinned, total + 64));
+    p->pinned_bytes = total + 64;
+    CUDA_TRY(ctx, cudaEventCreateWithFlags(&p->pinned_event, cudaEventDisableTiming));
+  }
   memcpy(p->pinned, pk.nodes.data(), p->nodes_bytes);
   memcpy(p->pinned + p->nodes_bytes, pk.nodes_soa.data(), p->nodes_bytes);
   memcpy(p->pinned + 2 * p->nodes_bytes, pk.geom.data(), p->geom_bytes);
   memcpy(p->pinned + 2 * p->nodes_bytes + p->geom_bytes, pk.colour.data(), p->colour_bytes);
-  CUDA_TRY(ctx, cudaMalloc(&p->d_nodes, p->nodes_bytes));
-  CUDA_TRY(ctx, cudaMalloc(&p->d_nodes_soa, p->nodes_bytes));
-  CUDA_TRY(ctx, cudaMalloc(&p->d_geom, p->geom_bytes));
-  CUDA_TRY(ctx, cudaMalloc(&p->d_colour, p->colour_bytes));
+  CUDA_TRY(ctx, cudaMallocAsync(&p->d_block, total, ctx->stream));
+  p->d_nodes = reinterpret_cast<float4 *>(p->d_block);
+  p->d_nodes_soa = reinterpret_cast<float4 *>(p->d_block + p->nodes_bytes);
+  p->d_geom = reinterpret_cast<float4 *>(p->d_block + 2 * p->nodes_bytes);
+  p->d_colour = reinterpret_cast<float4 *>(p->d_block + 2 * p->nodes_bytes + p->geom_bytes);
   return copy_prepared_h2d(ctx, p);  // completion: futhark_context_sync, or stream order for later renders
 }
 
@@ -416,6 +436,7 @@ void futhark_context_free(struct futhark_context *ctx) {
     cudaSetDevice(ctx->cfg.device);
     cudaStreamSynchronize(ctx->stream);
   }
+  for (auto &b : ctx->pinned_cache) { cudaEventDestroy(b.last_use); cudaFreeHost(b.ptr); }
   if (ctx->ok) free_wavefront(ctx);
   if (ctx->sample_buf) cudaFree(ctx->sample_buf);
   if (ctx->offsets) cudaFree(ctx->offsets);
@@ -555,8 +576,7 @@ int futhark_free_opaque_prepared_scene(struct futhark_context *ctx, struct futha
   if (!obj) return 0;
   if (ctx && ctx->ok) {
     std::lock_guard<std::mutex> g(ctx->mu);
-    cudaStreamSynchronize(ctx->stream);  // a render using it may still be in flight
-    free_prepared_device(obj);
+    free_prepared_device(ctx, obj);  // stream-ordered: a render still using it finishes first
   }
   delete obj;
   return 0;
@@ -617,7 +637,7 @@ int futhark_entry_prepare_scene(struct futhark_context *ctx, struct futhark_opaq
   std::string err;
   if (!build_lbvh(p->host, p->tree, &err)) { set_error(ctx, "%s", err.c_str()); delete p; return 1; }
   p->cam = make_camera(p->host, h, w);
-  if (upload_prepared(ctx, p)) { free_prepared_device(p); delete p; return 1; }
+  if (upload_prepared(ctx, p)) { free_prepared_device(ctx, p); delete p; return 1; }
   *out0 = p;
   return 0;
 }
