@@ -12,7 +12,7 @@ and equal the oracle's (tests/test_gpu_parity.py::test_work_counters_equal_refer
 
 Prints ONE JSON line (rank 0).  `value` = segments of all frames of a step / device time (scene
 resident in HBM, CUDA events, max over ranks); `e2e` = the same through host buffers: H2D of the packed
-scene from pinned memory + render + D2H of the frame into pinned memory, wall clock; `roofline` = the
+sphere records from pinned memory + LBVH build on the device + render + D2H of the frame into pinned memory, wall clock; `roofline` = the
 render kernel's algorithmic bytes (32 B x box tests + 16 B x sphere tests + 4 B x pixels, reference
 traversal counts) / its measured duration vs the measured HBM peak; `cpu_baseline` = the CPU oracle
 (a bit-exact port of the reference's Futhark program; the Futhark compiler is not available here) on a
@@ -289,12 +289,12 @@ def run_ours(args):
     e2e = None
     if world == 1:
         host = {n: torch.empty((H, W), dtype=torch.int32, pin_memory=True) for n in SCENES}
-        h2d = sum(prepared[n].device_bytes() for n in SCENES)
+        h2d = sum(prepared[n].upload_bytes() for n in SCENES)
         d2h = 4 * H * W * len(SCENES)
 
         def e2e_step():
             for name in SCENES:
-                prepared[name].reupload()                                   # H2D: packed BVH + spheres from pinned memory
+                prepared[name].reupload()                                   # H2D of the sphere records from pinned memory + device LBVH build
                 img = ctx.render(H, W, prepared[name], spp=SPP)             # futhark_entry_render-style call
                 ctx.lib.futhark_values_i32_2d(ctx.handle, img.handle, host[name].data_ptr())  # D2H + sync (main.c:130)
                 img.free()
@@ -325,7 +325,7 @@ def run_ours(args):
         tt = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": round(seg_per_step * args.steps / float(tt.item()) / 1e6, 1), "unit": "Mrays/s",
-               "h2d_bytes_per_step": sum(prepared[n].device_bytes() for n in SCENES), "d2h_bytes_per_step": 4 * H * W * len(SCENES),
+               "h2d_bytes_per_step": sum(prepared[n].upload_bytes() for n in SCENES), "d2h_bytes_per_step": 4 * H * W * len(SCENES),
                "ms_per_step": round(1e3 * float(tt.item()) / args.steps, 3)}
 
     # context: the reference's own published protocol (1 sample per pixel, README table) on this GPU

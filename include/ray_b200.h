@@ -75,10 +75,17 @@ int ray_b200_prepared_dump(struct futhark_context *ctx, const struct futhark_opa
                            uint32_t *morton, int32_t *perm, int32_t *left, int32_t *right, int32_t *parent,
                            float *boxes);
 
-/* Bytes of the packed scene resident in HBM (nodes + sphere geometry + colours). */
+/* The packed BVH2C arrays as they sit in HBM (tests compare device-built and host-built scenes):
+ * nodes / nodes_soa: (n-1) x 16 floats, geom / colour: n x 4 floats.  NULLs skipped.  Synchronous. */
+int ray_b200_prepared_packed(struct futhark_context *ctx, const struct futhark_opaque_prepared_scene *p, float *nodes,
+                             float *nodes_soa, float *geom, float *colour);
+/* Bytes prepare_scene copies host -> device: the sphere records (LBVH build and packing run on the device);
+ * with tuning "host_build" / RAY_HOST_BUILD=1 the host-built arrays instead. */
+int64_t ray_b200_prepared_upload_bytes(struct futhark_context *ctx, const struct futhark_opaque_prepared_scene *p);
+/* Bytes of the prepared scene resident in HBM (packed BVH2C + the Karras-order LBVH kept for introspection). */
 int64_t ray_b200_prepared_device_bytes(struct futhark_context *ctx, const struct futhark_opaque_prepared_scene *p);
-/* Copies the packed scene host -> device again from page-locked memory, asynchronously on the
- * context's stream (the H2D leg of an end-to-end step; prepare_scene already does it once). */
+/* Runs prepare_scene's device work again for an existing handle: H2D of the sphere records from page-locked
+ * memory + LBVH build on the device (the H2D leg of bench.py's end-to-end step). */
 int ray_b200_prepared_reupload(struct futhark_context *ctx, struct futhark_opaque_prepared_scene *p);
 
 /* ---- render extensions -------------------------------------------------------------------------- */

@@ -108,6 +108,8 @@ def load_library():
         "ray_b200_prepared_info": (C.c_int, [vp, vp, C.POINTER(BvhInfo)]),
         "ray_b200_prepared_dump": (C.c_int, [vp] * 8),
         "ray_b200_prepared_reupload": (C.c_int, [vp, vp]),
+        "ray_b200_prepared_packed": (C.c_int, [vp, vp, vp, vp, vp, vp]),
+        "ray_b200_prepared_upload_bytes": (i64, [vp, vp]),
         "ray_b200_prepared_device_bytes": (i64, [vp, vp]),
         "ray_b200_render_into": (C.c_int, [vp, vp, vp, i64, i64, i32, vp]),
         "ray_b200_render_host": (C.c_int, [vp, vp, vp, i64, i64, i32, vp]),
@@ -265,6 +267,18 @@ class PreparedScene(_Handle):
                                                             _ptr(out["perm"]), _ptr(out["left"]), _ptr(out["right"]),
                                                             _ptr(out["parent"]), _ptr(out["boxes"])))
         return out
+
+    def packed(self):
+        """The packed BVH2C arrays as they sit in HBM (nodes, nodes_soa, geom, colour)."""
+        n = int(self.info()["n_leaves"])
+        out = dict(nodes=np.empty((n - 1, 16), np.float32), nodes_soa=np.empty((4, n - 1, 4), np.float32),
+                   geom=np.empty((n, 4), np.float32), colour=np.empty((n, 4), np.float32))
+        self.ctx._check(self.ctx.lib.ray_b200_prepared_packed(self.ctx.handle, self.handle, _ptr(out["nodes"]),
+                                                              _ptr(out["nodes_soa"]), _ptr(out["geom"]), _ptr(out["colour"])))
+        return out
+
+    def upload_bytes(self):
+        return int(self.ctx.lib.ray_b200_prepared_upload_bytes(self.ctx.handle, self.handle))
 
     def device_bytes(self):
         return int(self.ctx.lib.ray_b200_prepared_device_bytes(self.ctx.handle, self.handle))

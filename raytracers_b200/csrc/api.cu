@@ -13,6 +13,7 @@
 #include <string>
 #include <vector>
 
+#include "bvh_build.h"
 #include "render_params.h"
 #include "scene_host.h"
 
@@ -26,7 +27,7 @@ struct futhark_context_config {
   int32_t kernel = RAY_B200_KERNEL_AUTO;
   int32_t rank = 0, world = 1;
   int32_t block_threads = 256, blocks_per_sm = 4, smem_budget = 48 * 1024, refill_min = 8, tail_from = 8;
-  int32_t wq_warps = 24, wq_k = 1, wq_spread = 1, permute = 1;
+  int32_t wq_warps = 24, wq_k = 1, wq_spread = 1, permute = 1, host_build = 0;
   std::string cache_file;
 };
 
@@ -47,6 +48,7 @@ struct futhark_context {
   WavefrontBuffers wf;                      // ray queues of the wavefront kernel (grown on demand)
   struct PinnedBlock { unsigned char *ptr; size_t bytes; cudaEvent_t last_use; };
   std::vector<PinnedBlock> pinned_cache;    // page-locked upload buffers of freed prepared scenes, reused by the next prepare_scene
+  BvhBuildResult *d_build_result = nullptr, *h_build_result = nullptr;  // device scratch / page-locked host mirror
   int32_t plan_wq_warps = 0;                // warps per CTA the warp-queue kernel will use for the frame being set up
   float4 *sample_buf = nullptr;             // warp-queue kernel, spp > 1: per-warp finished-sample colours
   size_t sample_buf_bytes = 0;
@@ -61,19 +63,17 @@ struct futhark_opaque_scene {
 };
 
 struct futhark_opaque_prepared_scene {
-  HostScene host;   // kept for store/restore
+  HostScene host;   // kept for store/restore and re-preparation
   int64_t h = 0, w = 0;
-  Lbvh tree;        // Karras-order LBVH (host copy, for introspection and store)
   CameraRec cam;
   float root_box[6];
-  int32_t max_depth = 0;
-  unsigned char *d_block = nullptr; // one stream-ordered device allocation holding the four arrays below
-  float4 *d_nodes = nullptr, *d_nodes_soa = nullptr, *d_geom = nullptr, *d_colour = nullptr;
-  unsigned char *pinned = nullptr;  // packed nodes | nodes_soa | geom | colour in page-locked host memory (upload source)
+  int32_t max_depth = 0, stale_nodes = 0, refit_sweeps = 0;
+  int64_t n = 0;
+  DeviceBvh dev;    // everything resident in HBM (one stream-ordered allocation): packed BVH2C + the Karras-order LBVH
+  unsigned char *pinned = nullptr;     // page-locked upload buffer (sphere records, or the host-built arrays)
   size_t pinned_bytes = 0;
   cudaEvent_t pinned_event = nullptr;  // completion of the last H2D copy that read `pinned`
-  size_t nodes_bytes = 0, geom_bytes = 0, colour_bytes = 0;
-  int64_t n = 0;
+  bool host_built = false;
 };
 
 struct futhark_i32_2d {
@@ -121,7 +121,7 @@ int parse_kernel(const char *v, int dflt) {
   return atoi(v);
 }
 
-const char *kTuningNames[] = {"kernel", "spp", "blocks_per_sm", "smem_budget", "refill_min", "tail_from", "wq_warps", "wq_k", "wq_spread", "permute", "rank", "world"};
+const char *kTuningNames[] = {"kernel", "spp", "blocks_per_sm", "smem_budget", "refill_min", "tail_from", "wq_warps", "wq_k", "wq_spread", "permute", "host_build", "rank", "world"};
 constexpr int kNumTuning = sizeof(kTuningNames) / sizeof(kTuningNames[0]);
 
 bool bad_ctx(futhark_context *ctx) { return ctx == nullptr || !ctx->ok; }
@@ -149,14 +149,14 @@ int resolve_kernel(const futhark_context *ctx);
 // Fills the kernel parameter block for one frame.
 int fill_params(futhark_context *ctx, const futhark_opaque_prepared_scene *p, int64_t h, int64_t w, int32_t spp,
                 int32_t rank, int32_t world, int32_t *out_pix, float *out_rgb, bool tile_major, RenderParams &P) {
-  if (!p || !p->d_nodes) { set_error(ctx, "render: invalid prepared scene"); return 1; }
+  if (!p || !p->dev.nodes) { set_error(ctx, "render: invalid prepared scene"); return 1; }
   if (h <= 0 || w <= 0 || h > 65536 || w > 65536) { set_error(ctx, "render: bad image size %lldx%lld", (long long)h, (long long)w); return 1; }
   if (spp < 1) { set_error(ctx, "render: spp must be >= 1"); return 1; }
   if (world < 1 || rank < 0 || rank >= world) { set_error(ctx, "render: bad shard %d/%d", rank, world); return 1; }
   if (p->max_depth > kStackSize - 1) { set_error(ctx, "render: BVH depth %d exceeds the traversal stack", p->max_depth); return 1; }
   if (ensure_offsets(ctx, spp)) return 1;
   memset(&P, 0, sizeof P);
-  P.nodes = p->d_nodes; P.nodes_soa = p->d_nodes_soa; P.geom = p->d_geom; P.colour = p->d_colour;
+  P.nodes = p->dev.nodes; P.nodes_soa = p->dev.nodes_soa; P.geom = p->dev.geom; P.colour = p->dev.colour;
   P.n_inner = (int32_t)(p->n - 1); P.n_leaves = (int32_t)p->n;
   P.max_depth = p->max_depth;
   memcpy(P.root_box, p->root_box, sizeof P.root_box);
@@ -280,60 +280,112 @@ int do_render(futhark_context *ctx, RenderParams &P) {
 // Device memory goes back to the stream-ordered pool (ordered after any render still using it);
 // the page-locked upload buffer goes to the context's cache together with the event that guards it.
 void free_prepared_device(futhark_context *ctx, futhark_opaque_prepared_scene *p) {
-  if (p->d_block) cudaFreeAsync(p->d_block, ctx->stream);
+  if (p->dev.block) cudaFreeAsync(p->dev.block, ctx->stream);
   if (p->pinned) {
     if (ctx->pinned_cache.size() < 4) ctx->pinned_cache.push_back({p->pinned, p->pinned_bytes, p->pinned_event});
     else { cudaEventSynchronize(p->pinned_event); cudaEventDestroy(p->pinned_event); cudaFreeHost(p->pinned); }
   }
-  p->d_block = nullptr;
-  p->d_nodes = p->d_nodes_soa = p->d_geom = p->d_colour = nullptr;
+  p->dev = DeviceBvh();
   p->pinned = nullptr;
   p->pinned_event = nullptr;
 }
 
-// Host -> device copy of the packed scene from page-locked memory (asynchronous on the context stream).
-int copy_prepared_h2d(futhark_context *ctx, futhark_opaque_prepared_scene *p) {
-  const size_t total = 2 * p->nodes_bytes + p->geom_bytes + p->colour_bytes;
-  CUDA_TRY(ctx, cudaMemcpyAsync(p->d_block, p->pinned, total, cudaMemcpyHostToDevice, ctx->stream));
-  CUDA_TRY(ctx, cudaEventRecord(p->pinned_event, ctx->stream));
+// A page-locked staging buffer of at least `bytes`, reusing a cached one when possible (main.c frees and
+// re-prepares the same scene every run).
+int acquire_pinned(futhark_context *ctx, futhark_opaque_prepared_scene *p, size_t bytes) {
+  if (p->pinned && p->pinned_bytes >= bytes) {
+    CUDA_TRY(ctx, cudaEventSynchronize(p->pinned_event));
+    return 0;
+  }
+  if (p->pinned) {
+    CUDA_TRY(ctx, cudaEventSynchronize(p->pinned_event));
+    CUDA_TRY(ctx, cudaFreeHost(p->pinned));
+    p->pinned = nullptr;
+  }
+  for (size_t k = 0; k < ctx->pinned_cache.size(); k++) {
+    auto &b = ctx->pinned_cache[k];
+    if (b.bytes >= bytes && b.bytes <= 2 * bytes + 4096) {
+      CUDA_TRY(ctx, cudaEventSynchronize(b.last_use));  // the copy that last read this block has finished
+      if (p->pinned_event) cudaEventDestroy(p->pinned_event);
+      p->pinned = b.ptr; p->pinned_bytes = b.bytes; p->pinned_event = b.last_use;
+      ctx->pinned_cache.erase(ctx->pinned_cache.begin() + (long)k);
+      return 0;
+    }
+  }
+  CUDA_TRY(ctx, cudaMallocHost(&p->pinned, bytes + 64));
+  p->pinned_bytes = bytes + 64;
+  if (!p->pinned_event) CUDA_TRY(ctx, cudaEventCreateWithFlags(&p->pinned_event, cudaEventDisableTiming));
   return 0;
 }
 
-int upload_prepared(futhark_context *ctx, futhark_opaque_prepared_scene *p) {
+// prepare_scene, device path (default): H2D of the sphere records from page-locked memory, then the whole
+// LBVH build + packing as kernels on the context's stream (bvh_build.cu).
+int prepare_on_device(futhark_context *ctx, futhark_opaque_prepared_scene *p) {
+  const size_t n = p->host.spheres.size();
+  const size_t sph_bytes = n * sizeof(SphereRec);
+  if (acquire_pinned(ctx, p, sph_bytes)) return 1;
+  memcpy(p->pinned, p->host.spheres.data(), sph_bytes);
+  float *d_spheres = nullptr;
+  CUDA_TRY(ctx, cudaMallocAsync(&d_spheres, sph_bytes, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(d_spheres, p->pinned, sph_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaEventRecord(p->pinned_event, ctx->stream));
+  p->refit_sweeps = (int32_t)log2f((float)(int64_t)n) + 2;  // bvh.fut:47, host libm as in the reference's C backend
+  if (p->dev.block) { CUDA_TRY(ctx, cudaFreeAsync(p->dev.block, ctx->stream)); p->dev = DeviceBvh(); }
+  CUDA_TRY(ctx, build_bvh_device(d_spheres, (int64_t)n, p->refit_sweeps, p->dev, ctx->d_build_result, ctx->stream, &ctx->launches));
+  CUDA_TRY(ctx, cudaFreeAsync(d_spheres, ctx->stream));
+  // the host needs the tree depth (stack sizing) and the root box (kernel parameter) before the first render
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_build_result, ctx->d_build_result, sizeof(BvhBuildResult), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(p->root_box, ctx->h_build_result->root_box, sizeof p->root_box);
+  p->max_depth = ctx->h_build_result->max_depth;
+  p->stale_nodes = ctx->h_build_result->stale_nodes;
+  p->n = (int64_t)n;
+  p->host_built = false;
+  return 0;
+}
+
+// prepare_scene, host path (RAY_HOST_BUILD=1 / tuning "host_build"): scene_host.cpp builds and packs, one H2D copy.
+// Kept as an independent implementation the device path is tested against.
+int prepare_on_host(futhark_context *ctx, futhark_opaque_prepared_scene *p) {
+  Lbvh tree;
+  std::string err;
+  if (!build_lbvh(p->host, tree, &err)) { set_error(ctx, "%s", err.c_str()); return 1; }
   PackedBvh pk;
-  pack_bvh(p->host, p->tree, pk);
+  pack_bvh(p->host, tree, pk);
+  const int64_t n = tree.n;
+  const size_t total = device_bvh_bytes(n);
+  if (acquire_pinned(ctx, p, total)) return 1;
+  DeviceBvh hostside;  // the same carving, applied to the page-locked buffer
+  carve_device_bvh(p->pinned, n, hostside);
+  const size_t ni = (size_t)(n - 1);
+  memcpy(hostside.nodes, pk.nodes.data(), ni * 64);
+  memcpy(hostside.nodes_soa, pk.nodes_soa.data(), ni * 64);
+  memcpy(hostside.geom, pk.geom.data(), (size_t)n * 16);
+  memcpy(hostside.colour, pk.colour.data(), (size_t)n * 16);
+  memcpy(hostside.morton, tree.morton.data(), (size_t)n * 4);
+  memcpy(hostside.perm, tree.perm.data(), (size_t)n * 4);
+  memcpy(hostside.left, tree.left.data(), ni * 4);
+  memcpy(hostside.right, tree.right.data(), ni * 4);
+  memcpy(hostside.parent, tree.parent.data(), ni * 4);
+  memcpy(hostside.boxes, tree.boxes.data(), ni * 24);
+  if (p->dev.block) { CUDA_TRY(ctx, cudaFreeAsync(p->dev.block, ctx->stream)); p->dev = DeviceBvh(); }
+  unsigned char *blk = nullptr;
+  CUDA_TRY(ctx, cudaMallocAsync(&blk, total, ctx->stream));
+  carve_device_bvh(blk, n, p->dev);
+  CUDA_TRY(ctx, cudaMemcpyAsync(blk, p->pinned, total, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaEventRecord(p->pinned_event, ctx->stream));
   memcpy(p->root_box, pk.root_box, sizeof p->root_box);
-  p->max_depth = pk.max_depth;
-  p->n = p->tree.n;
-  p->nodes_bytes = pk.nodes.size() * sizeof(F4);
-  p->geom_bytes = pk.geom.size() * sizeof(F4);
-  p->colour_bytes = pk.colour.size() * sizeof(F4);
-  const size_t total = 2 * p->nodes_bytes + p->geom_bytes + p->colour_bytes;  // every part is a multiple of 16 B
-  // page-locked staging: reuse a cached block (main.c frees and re-prepares the same scene every run)
-  for (size_t k = 0; k < ctx->pinned_cache.size(); k++) {
-    auto &b = ctx->pinned_cache[k];
-    if (b.bytes >= total && b.bytes <= 2 * total + 4096) {
-      CUDA_TRY(ctx, cudaEventSynchronize(b.last_use));  // the copy that last read this block has finished
-      p->pinned = b.ptr; p->pinned_bytes = b.bytes; p->pinned_event = b.last_use;
-      ctx->pinned_cache.erase(ctx->pinned_cache.begin() + (long)k);
-      break;
-    }
-  }
-  if (!p->pinned) {
-    CUDA_TRY(ctx, cudaMallocHost(&p->pinned, total + 64));
-    p->pinned_bytes = total + 64;
-    CUDA_TRY(ctx, cudaEventCreateWithFlags(&p->pinned_event, cudaEventDisableTiming));
-  }
-  memcpy(p->pinned, pk.nodes.data(), p->nodes_bytes);
-  memcpy(p->pinned + p->nodes_bytes, pk.nodes_soa.data(), p->nodes_bytes);
-  memcpy(p->pinned + 2 * p->nodes_bytes, pk.geom.data(), p->geom_bytes);
-  memcpy(p->pinned + 2 * p->nodes_bytes + p->geom_bytes, pk.colour.data(), p->colour_bytes);
-  CUDA_TRY(ctx, cudaMallocAsync(&p->d_block, total, ctx->stream));
-  p->d_nodes = reinterpret_cast<float4 *>(p->d_block);
-  p->d_nodes_soa = reinterpret_cast<float4 *>(p->d_block + p->nodes_bytes);
-  p->d_geom = reinterpret_cast<float4 *>(p->d_block + 2 * p->nodes_bytes);
-  p->d_colour = reinterpret_cast<float4 *>(p->d_block + 2 * p->nodes_bytes + p->geom_bytes);
-  return copy_prepared_h2d(ctx, p);  // completion: futhark_context_sync, or stream order for later renders
+  p->max_depth = tree.max_depth; p->stale_nodes = tree.stale_nodes; p->refit_sweeps = tree.refit_sweeps;
+  p->n = n;
+  p->host_built = true;
+  return 0;
+}
+
+int prepare_any(futhark_context *ctx, futhark_opaque_prepared_scene *p) {
+  const int64_t n = (int64_t)p->host.spheres.size();
+  if (n < 2) { set_error(ctx, "prepare_scene: a scene needs at least 2 spheres (the reference indexes I[0], bvh.fut:65)"); return 1; }
+  if (n > (int64_t)1 << 26) { set_error(ctx, "prepare_scene: too many spheres (this build packs leaf indices into 26 bits)"); return 1; }
+  return ctx->cfg.host_build ? prepare_on_host(ctx, p) : prepare_on_device(ctx, p);
 }
 
 }  // namespace
@@ -369,6 +421,7 @@ int futhark_context_config_set_tuning_param(struct futhark_context_config *cfg, 
   else if (!strcmp(name, "wq_k")) cfg->wq_k = (int32_t)v;
   else if (!strcmp(name, "wq_spread")) cfg->wq_spread = (int32_t)v;
   else if (!strcmp(name, "permute")) cfg->permute = (int32_t)v;
+  else if (!strcmp(name, "host_build")) cfg->host_build = (int32_t)v;
   else if (!strcmp(name, "rank")) cfg->rank = (int32_t)v;
   else if (!strcmp(name, "world")) cfg->world = (int32_t)v;
   else return 1;
@@ -393,6 +446,7 @@ struct futhark_context *futhark_context_new(struct futhark_context_config *cfg) 
   ctx->cfg.wq_k = env_int("RAY_WQ_K", ctx->cfg.wq_k);
   ctx->cfg.wq_spread = env_int("RAY_WQ_SPREAD", ctx->cfg.wq_spread);
   ctx->cfg.permute = env_int("RAY_PERMUTE", ctx->cfg.permute);
+  ctx->cfg.host_build = env_int("RAY_HOST_BUILD", ctx->cfg.host_build);
   memset(&ctx->wf, 0, sizeof ctx->wf);
 
   auto fail = [&](const char *what, cudaError_t e) {
@@ -419,6 +473,8 @@ struct futhark_context *futhark_context_new(struct futhark_context_config *cfg) 
   if ((e = cudaEventCreate(&ctx->ev_stop)) != cudaSuccess) return fail("cudaEventCreate", e);
   if ((e = cudaMalloc(&ctx->work_cursor, 64)) != cudaSuccess) return fail("cudaMalloc", e);
   if ((e = cudaMalloc(&ctx->counters, 4 * sizeof(unsigned long long))) != cudaSuccess) return fail("cudaMalloc", e);
+  if ((e = cudaMalloc(&ctx->d_build_result, sizeof(BvhBuildResult))) != cudaSuccess) return fail("cudaMalloc", e);
+  if ((e = cudaMallocHost(&ctx->h_build_result, sizeof(BvhBuildResult))) != cudaSuccess) return fail("cudaMallocHost", e);
   if ((e = configure_kernels(ctx->max_smem_optin)) != cudaSuccess) return fail("cudaFuncSetAttribute", e);
   // keep freed frames in the stream-ordered pool: futhark/main.c frees and re-allocates the image every run
   cudaMemPool_t pool;
@@ -442,6 +498,8 @@ void futhark_context_free(struct futhark_context *ctx) {
   if (ctx->offsets) cudaFree(ctx->offsets);
   if (ctx->work_cursor) cudaFree(ctx->work_cursor);
   if (ctx->counters) cudaFree(ctx->counters);
+  if (ctx->d_build_result) cudaFree(ctx->d_build_result);
+  if (ctx->h_build_result) cudaFreeHost(ctx->h_build_result);
   if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
   if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -634,10 +692,8 @@ int futhark_entry_prepare_scene(struct futhark_context *ctx, struct futhark_opaq
   futhark_opaque_prepared_scene *p = new futhark_opaque_prepared_scene;
   p->host = scene->host;
   p->h = h; p->w = w;
-  std::string err;
-  if (!build_lbvh(p->host, p->tree, &err)) { set_error(ctx, "%s", err.c_str()); delete p; return 1; }
   p->cam = make_camera(p->host, h, w);
-  if (upload_prepared(ctx, p)) { free_prepared_device(ctx, p); delete p; return 1; }
+  if (prepare_any(ctx, p)) { free_prepared_device(ctx, p); delete p; return 1; }
   *out0 = p;
   return 0;
 }
@@ -741,7 +797,7 @@ int ray_b200_prepared_info(struct futhark_context *ctx, const struct futhark_opa
   if (bad_ctx(ctx) || !p || !info) return 1;
   memset(info, 0, sizeof *info);
   info->n_leaves = p->n; info->n_inner = p->n - 1;
-  info->max_depth = p->tree.max_depth; info->refit_sweeps = p->tree.refit_sweeps; info->stale_nodes = p->tree.stale_nodes;
+  info->max_depth = p->max_depth; info->refit_sweeps = p->refit_sweeps; info->stale_nodes = p->stale_nodes;
   RenderParams P;
   std::lock_guard<std::mutex> g(ctx->mu);
   if (fill_params(ctx, p, 8, 8, 1, 0, 1, nullptr, nullptr, false, P) == 0) info->smem_nodes = P.smem_nodes;
@@ -751,28 +807,52 @@ int ray_b200_prepared_info(struct futhark_context *ctx, const struct futhark_opa
 }
 int ray_b200_prepared_dump(struct futhark_context *ctx, const struct futhark_opaque_prepared_scene *p, uint32_t *morton, int32_t *perm,
                            int32_t *left, int32_t *right, int32_t *parent, float *boxes) {
-  (void)ctx;
-  if (!p) return 1;
-  const Lbvh &t = p->tree;
-  if (morton) memcpy(morton, t.morton.data(), t.morton.size() * 4);
-  if (perm) memcpy(perm, t.perm.data(), t.perm.size() * 4);
-  if (left) memcpy(left, t.left.data(), t.left.size() * 4);
-  if (right) memcpy(right, t.right.data(), t.right.size() * 4);
-  if (parent) memcpy(parent, t.parent.data(), t.parent.size() * 4);
-  if (boxes) memcpy(boxes, t.boxes.data(), t.boxes.size() * 4);
+  if (bad_ctx(ctx)) return 1;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (!p || !p->dev.block) { set_error(ctx, "prepared_dump: invalid prepared scene"); return 1; }
+  const size_t n = (size_t)p->n, ni = n - 1;
+  const cudaMemcpyKind k = cudaMemcpyDeviceToHost;
+  if (morton) CUDA_TRY(ctx, cudaMemcpyAsync(morton, p->dev.morton, n * 4, k, ctx->stream));
+  if (perm) CUDA_TRY(ctx, cudaMemcpyAsync(perm, p->dev.perm, n * 4, k, ctx->stream));
+  if (left) CUDA_TRY(ctx, cudaMemcpyAsync(left, p->dev.left, ni * 4, k, ctx->stream));
+  if (right) CUDA_TRY(ctx, cudaMemcpyAsync(right, p->dev.right, ni * 4, k, ctx->stream));
+  if (parent) CUDA_TRY(ctx, cudaMemcpyAsync(parent, p->dev.parent, ni * 4, k, ctx->stream));
+  if (boxes) CUDA_TRY(ctx, cudaMemcpyAsync(boxes, p->dev.boxes, ni * 24, k, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+// The packed BVH2C arrays as they sit in HBM: nodes[(n-1)*16 floats], nodes_soa[same], geom[n*4], colour[n*4]. NULLs skipped.
+int ray_b200_prepared_packed(struct futhark_context *ctx, const struct futhark_opaque_prepared_scene *p, float *nodes, float *nodes_soa,
+                             float *geom, float *colour) {
+  if (bad_ctx(ctx)) return 1;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (!p || !p->dev.block) { set_error(ctx, "prepared_packed: invalid prepared scene"); return 1; }
+  const size_t n = (size_t)p->n, ni = n - 1;
+  const cudaMemcpyKind k = cudaMemcpyDeviceToHost;
+  if (nodes) CUDA_TRY(ctx, cudaMemcpyAsync(nodes, p->dev.nodes, ni * 64, k, ctx->stream));
+  if (nodes_soa) CUDA_TRY(ctx, cudaMemcpyAsync(nodes_soa, p->dev.nodes_soa, ni * 64, k, ctx->stream));
+  if (geom) CUDA_TRY(ctx, cudaMemcpyAsync(geom, p->dev.geom, n * 16, k, ctx->stream));
+  if (colour) CUDA_TRY(ctx, cudaMemcpyAsync(colour, p->dev.colour, n * 16, k, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return 0;
 }
 
 int ray_b200_prepared_reupload(struct futhark_context *ctx, struct futhark_opaque_prepared_scene *p) {
   if (bad_ctx(ctx)) return 1;
   std::lock_guard<std::mutex> g(ctx->mu);
-  if (!p || !p->pinned) { set_error(ctx, "prepared_reupload: invalid prepared scene"); return 1; }
+  if (!p || !p->dev.block) { set_error(ctx, "prepared_reupload: invalid prepared scene"); return 1; }
   CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
-  return copy_prepared_h2d(ctx, p);
+  return prepare_any(ctx, p);  // H2D of the sphere records again + the device LBVH build (or the host path)
 }
 int64_t ray_b200_prepared_device_bytes(struct futhark_context *ctx, const struct futhark_opaque_prepared_scene *p) {
   (void)ctx;
-  return p ? (int64_t)(2 * p->nodes_bytes + p->geom_bytes + p->colour_bytes) : -1;
+  return p ? (int64_t)p->dev.block_bytes : -1;
+}
+// Bytes prepare_scene / prepared_reupload copy host -> device (the sphere records on the device-build path).
+int64_t ray_b200_prepared_upload_bytes(struct futhark_context *ctx, const struct futhark_opaque_prepared_scene *p) {
+  (void)ctx;
+  if (!p) return -1;
+  return p->host_built ? (int64_t)p->dev.block_bytes : (int64_t)(p->host.spheres.size() * sizeof(SphereRec));
 }
 
 int ray_b200_render_into(struct futhark_context *ctx, int32_t *out_pix_dev, float *out_rgb_dev, int64_t h, int64_t w, int32_t spp,

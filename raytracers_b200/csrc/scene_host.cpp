@@ -301,6 +301,7 @@ bool build_lbvh(const HostScene &s, Lbvh &t, std::string *err) {
       if (ch[c] >= 0) { depth[(size_t)ch[c]] = dk + 1; order.push_back(ch[c]); }
   }
   t.max_depth = maxd;
+  t.depth = depth;
   if ((int64_t)order.size() != ni) {
     if (err) *err = "prepare_scene: internal error, radix tree is not connected";
     return false;
@@ -311,16 +312,12 @@ bool build_lbvh(const HostScene &s, Lbvh &t, std::string *err) {
 void pack_bvh(const HostScene &s, const Lbvh &t, PackedBvh &out) {
   const int64_t n = t.n;
   const int32_t ni = (int32_t)(n - 1);
-  // BFS order: the first K packed nodes are the top of the tree (what the kernels stage in shared memory)
-  std::vector<int32_t> order, newidx((size_t)ni, -1);
-  order.reserve((size_t)ni);
-  order.push_back(0);
-  for (size_t head = 0; head < order.size(); head++) {
-    const int32_t k = order[head];
-    newidx[(size_t)k] = (int32_t)head;
-    if (t.left[(size_t)k] >= 0) order.push_back(t.left[(size_t)k]);
-    if (t.right[(size_t)k] >= 0) order.push_back(t.right[(size_t)k]);
-  }
+  // nodes ordered by (depth, Karras index): the first K packed nodes are the top of the tree (what the kernels
+  // stage in shared memory); identical to the order the device builder produces with a stable sort by depth
+  std::vector<int32_t> order((size_t)ni), newidx((size_t)ni, -1);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return t.depth[(size_t)a] < t.depth[(size_t)b]; });
+  for (int32_t pos = 0; pos < ni; pos++) newidx[(size_t)order[(size_t)pos]] = pos;
   out.nodes.resize((size_t)ni * 4);
   const float inf = std::numeric_limits<float>::infinity();
   auto as_float = [](int32_t v) { float f; std::memcpy(&f, &v, 4); return f; };

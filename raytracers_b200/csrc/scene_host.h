@@ -33,10 +33,12 @@ struct Lbvh {
   std::vector<int32_t> left, right;   // child pointers: inner i -> i, leaf i -> ~i (bvh.fut:24)
   std::vector<int32_t> parent;        // parent(root) = -1 (radixtree.fut:66-70)
   std::vector<float> boxes;           // (n-1) x {min.xyz, max.xyz} after the fixed-count Jacobi refit (bvh.fut:47-58)
+  std::vector<int32_t> depth;         // depth of every inner node, root = 0
   int32_t refit_sweeps = 0, max_depth = 0, stale_nodes = 0;
 };
 
-// Device layout ("BVH2C": both child boxes stored in the parent, nodes in BFS order).
+// Device layout ("BVH2C": both child boxes stored in the parent; nodes ordered by (depth, Karras index), so the
+// first K records are the top of the tree — the device builder in bvh_build.cu produces the same order).
 // Inner node k = 4 x float4:
 //   q0 = {Lmin.x, Lmin.y, Lmin.z, bits(left)}   q1 = {Lmax.x, Lmax.y, Lmax.z, bits(right)}
 //   q2 = {Rmin.x, Rmin.y, Rmin.z, 0}            q3 = {Rmax.x, Rmax.y, Rmax.z, 0}

@@ -155,6 +155,46 @@ def test_prepare_aspect_differs_from_render_size(R, oracle):
         assert_same(ctx.render_host(64, 80, pr), want, "aspect from prepare_scene")
 
 
+@pytest.mark.parametrize("name,kw", [("rgbbox", {}), ("irreg", {}), ("random", {"n": 30000, "seed": 4}), ("random", {"n": 2, "seed": 1}),
+                                     ("random", {"n": 3, "seed": 2}), ("random", {"n": 1000, "seed": 8})])
+def test_device_lbvh_build_is_bit_identical_to_host_and_oracle(R, oracle, name, kw):
+    """prepare_scene runs on the device (bvh_build.cu): Morton keys, stable sort, Karras tree, fixed-count Jacobi refit
+    and the packed layout must equal the host builder's (scene_host.cpp) and the oracle's arrays bit for bit."""
+    s, c = R.host_scene(name, **kw)
+    want = oracle.Scene.custom(s, c).prepare(120, 200).dump()
+    host = R.host_lbvh(s)
+    with R.Context() as ctx, R.Context(host_build=1) as ctx_h:
+        pr = ctx.prepare_scene(120, 200, ctx.scene_from_arrays(s, c))
+        pr_h = ctx_h.prepare_scene(120, 200, ctx_h.scene_from_arrays(s, c))
+        got, got_h = pr.dump(), pr_h.dump()
+        for k in ("morton", "perm", "left", "right", "parent"):
+            np.testing.assert_array_equal(got[k], want[k], err_msg=f"device {k}")
+            np.testing.assert_array_equal(got_h[k], want[k], err_msg=f"host {k}")
+        np.testing.assert_array_equal(got["boxes"].view(np.uint32), want["boxes"].view(np.uint32))
+        info, info_h = pr.info(), pr_h.info()
+        for k in ("max_depth", "refit_sweeps", "stale_nodes"):
+            assert info[k] == info_h[k] == host[k], k
+        np.testing.assert_array_equal(info["root_box"].view(np.uint32), info_h["root_box"].view(np.uint32))
+        np.testing.assert_array_equal(info["camera"].view(np.uint32), want["cam"].view(np.uint32))
+        pk, pk_h = pr.packed(), pr_h.packed()
+        for k in ("nodes", "nodes_soa", "geom", "colour"):
+            np.testing.assert_array_equal(pk[k].view(np.uint32), pk_h[k].view(np.uint32), err_msg=f"packed {k}")
+        assert pr.upload_bytes() == s.nbytes and pr_h.upload_bytes() == pr_h.device_bytes()
+
+
+def test_degenerate_scenes_on_the_device_builder(R, oracle):
+    cam = np.float32([0, 0, 20, 0, 0, 0, 60])
+    same = np.tile(np.float32([1, 2, 3, 1, 1, 1, 0.5]), (37, 1))       # every Morton code equal: split purely by index
+    flat = np.float32([[x, 0, z, 1, 1, 1, 0.4] for x in range(-3, 4) for z in range(-3, 4)])  # flat axis: 0/0 -> NaN -> 0
+    for s in (same, flat):
+        want = oracle.Scene.custom(s, cam).prepare(32, 32).dump()
+        with R.Context() as ctx:
+            got = ctx.prepare_scene(32, 32, ctx.scene_from_arrays(s, cam)).dump()
+        for k in ("morton", "perm", "left", "right", "parent"):
+            np.testing.assert_array_equal(got[k], want[k], err_msg=k)
+        np.testing.assert_array_equal(got["boxes"].view(np.uint32), want["boxes"].view(np.uint32))
+
+
 def test_work_counters_equal_reference_traversal(R, oracle):
     """The GPU traversal visits exactly the reference's set of boxes and leaves (roofline numerators)."""
     for name, size in (("rgbbox", 200), ("irreg", 200)):
