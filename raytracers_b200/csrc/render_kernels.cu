@@ -13,6 +13,7 @@
 #include "device_math.cuh"
 
 #include <cstdio>
+#include <type_traits>
 
 namespace rayb200 {
 
@@ -745,63 +746,74 @@ __global__ void __launch_bounds__(768, 1) render_warpqueue_kernel(const __grid_c
     }
 
     // ---------------------------------------------------------------- dense traversal of the round
-    while (ntop > 0 || ltop > 0) {
-      if (ltop >= 32 || ntop == 0) {
-        // ---- leaf batch: closest_hit (ray.fut:78-81) for 32 (ray, sphere) pairs
-        const int n = ltop < 32 ? ltop : 32;
-        if (lane < n) {
-          const uint32_t it = lstk[ltop - 1 - lane];
-          const int slot = (int)(it >> kSlotShift), li = (int)(it & kIndexMask);
-          const float4 ro = ray_o[slot], rd = ray_d[slot];
-          const float4 g = sc.sphere(li);
-          Ray r;
-          r.o = v3(ro.x, ro.y, ro.z);
-          r.d = v3(rd.x, rd.y, rd.z);
-          const float t = sphere_t(g.x, g.y, g.z, g.w, r, ro.w, 0.1f, 1000000000.0f);
-          if (t >= 0.0f) atomicMin(best + slot, ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)li);
-        }
-        ltop -= n;
-      } else {
-        // ---- node batch: one BVH2C node step (both children's boxes) for up to 32 (ray, node) pairs
-        const int n = ntop < 32 ? ntop : 32;
-        bool pl_node = false, pr_node = false, pl_leaf = false, pr_leaf = false;
-        uint32_t tag = 0;
-        int lptr = 0, rptr = 0;
-        if (lane < n) {
-          const uint32_t it = nstk[ntop - 1 - lane];
-          tag = it & ~kIndexMask;
-          const int slot = (int)(it >> kSlotShift), cur = (int)(it & kIndexMask);
-          const float4 ro = ray_o[slot], ri = ray_i[slot];
-          float4 q0, q1, q2, q3;
-          sc.node(cur, q0, q1, q2, q3);
-          Ray r;
-          r.o = v3(ro.x, ro.y, ro.z);
-          r.d = v3(0.0f, 0.0f, 0.0f);
-          RayInv q;
-          q.ix = ri.x; q.iy = ri.y; q.iz = ri.z; q.a = ro.w;
-          lptr = __float_as_int(q0.w);
-          rptr = __float_as_int(q1.w);
-          const bool hl = box_hit(q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, r, q);
-          const bool hr = box_hit(q2.x, q2.y, q2.z, q3.x, q3.y, q3.z, r, q);
-          pl_leaf = lptr < 0;          // a leaf child has no box in the reference: always visited
-          pr_leaf = rptr < 0;
-          pl_node = hl && !pl_leaf;
-          pr_node = hr && !pr_leaf;
-        }
-        __syncwarp();  // all pops have been read before anything is pushed over them
-        ntop -= n;
-        const unsigned bl = __ballot_sync(kFullMask, pl_node), br = __ballot_sync(kFullMask, pr_node);
-        const unsigned cl = __ballot_sync(kFullMask, pl_leaf), cr = __ballot_sync(kFullMask, pr_leaf);
-        // reverse lane order: lane 0 popped the top (deepest) item, its children go back on top
-        const int nb = ntop + __popc(bl & gt_mask) + __popc(br & gt_mask);
-        if (pr_node) nstk[nb] = tag | (uint32_t)rptr;
-        if (pl_node) nstk[nb + (pr_node ? 1 : 0)] = tag | (uint32_t)lptr;
-        ntop += __popc(bl) + __popc(br);
-        const int lb = ltop + __popc(cl & lt_mask) + __popc(cr & lt_mask);
-        if (pl_leaf) lstk[lb] = tag | (uint32_t)(~lptr);
-        if (pr_leaf) lstk[lb + (pl_leaf ? 1 : 0)] = tag | (uint32_t)(~rptr);
-        ltop += __popc(cl) + __popc(cr);
+    // Both batch bodies exist twice: a full-warp version (32 items, no lane predicate: the four push flags stay in
+    // predicate registers) used while the stacks are deep enough, and a partial version for the drain.
+    auto leaf_batch = [&](auto full_tag) {
+      // closest_hit (ray.fut:78-81) for up to 32 (ray, sphere) pairs
+      constexpr bool kFull = decltype(full_tag)::value;
+      const int n = kFull ? 32 : ltop;
+      if (kFull || lane < n) {
+        const uint32_t it = lstk[ltop - 1 - lane];
+        const int slot = (int)(it >> kSlotShift), li = (int)(it & kIndexMask);
+        const float4 ro = ray_o[slot], rd = ray_d[slot];
+        const float4 g = sc.sphere(li);
+        Ray r;
+        r.o = v3(ro.x, ro.y, ro.z);
+        r.d = v3(rd.x, rd.y, rd.z);
+        const float t = sphere_t(g.x, g.y, g.z, g.w, r, ro.w, 0.1f, 1000000000.0f);
+        if (t >= 0.0f) atomicMin(best + slot, ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)li);
       }
+      ltop -= n;
+    };
+    auto node_batch = [&](auto full_tag) {
+      // one BVH2C node step (both children's boxes) for up to 32 (ray, node) pairs
+      constexpr bool kFull = decltype(full_tag)::value;
+      const int n = kFull ? 32 : ntop;
+      bool pl_node = false, pr_node = false, pl_leaf = false, pr_leaf = false;
+      uint32_t tag = 0;
+      int lptr = 0, rptr = 0;
+      if (kFull || lane < n) {
+        const uint32_t it = nstk[ntop - 1 - lane];
+        tag = it & ~kIndexMask;
+        const int slot = (int)(it >> kSlotShift), cur = (int)(it & kIndexMask);
+        const float4 ro = ray_o[slot], ri = ray_i[slot];
+        float4 q0, q1, q2, q3;
+        sc.node(cur, q0, q1, q2, q3);
+        Ray r;
+        r.o = v3(ro.x, ro.y, ro.z);
+        r.d = v3(0.0f, 0.0f, 0.0f);
+        RayInv q;
+        q.ix = ri.x; q.iy = ri.y; q.iz = ri.z; q.a = ro.w;
+        lptr = __float_as_int(q0.w);
+        rptr = __float_as_int(q1.w);
+        const bool hl = box_hit(q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, r, q);
+        const bool hr = box_hit(q2.x, q2.y, q2.z, q3.x, q3.y, q3.z, r, q);
+        pl_leaf = lptr < 0;          // a leaf child has no box in the reference: always visited
+        pr_leaf = rptr < 0;
+        pl_node = hl && !pl_leaf;
+        pr_node = hr && !pr_leaf;
+      }
+      __syncwarp();  // all pops have been read before anything is pushed over them
+      ntop -= n;
+      const unsigned bl = __ballot_sync(kFullMask, pl_node), br = __ballot_sync(kFullMask, pr_node);
+      const unsigned cl = __ballot_sync(kFullMask, pl_leaf), cr = __ballot_sync(kFullMask, pr_leaf);
+      // reverse lane order: lane 0 popped the top (deepest) item, its children go back on top
+      const int nb = ntop + __popc(bl & gt_mask) + __popc(br & gt_mask);
+      if (pr_node) nstk[nb] = tag | (uint32_t)rptr;
+      if (pl_node) nstk[nb + (pr_node ? 1 : 0)] = tag | (uint32_t)lptr;
+      ntop += __popc(bl) + __popc(br);
+      const int lb = ltop + __popc(cl & lt_mask) + __popc(cr & lt_mask);
+      if (pl_leaf) lstk[lb] = tag | (uint32_t)(~lptr);
+      if (pr_leaf) lstk[lb + (pl_leaf ? 1 : 0)] = tag | (uint32_t)(~rptr);
+      ltop += __popc(cl) + __popc(cr);
+    };
+    using full_t = std::integral_constant<bool, true>;
+    using part_t = std::integral_constant<bool, false>;
+    while (ntop > 0 || ltop > 0) {
+      if (ltop >= 32) leaf_batch(full_t{});
+      else if (ntop >= 32) node_batch(full_t{});
+      else if (ntop > 0) node_batch(part_t{});
+      else leaf_batch(part_t{});
       __syncwarp();
     }
 
