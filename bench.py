@@ -222,14 +222,11 @@ def run_ours(args):
     frames = {n: torch.empty((H, W), dtype=torch.int32, device="cuda") for n in SCENES}
     sharded = D.ShardedRenderer(ctx, rank, world) if world > 1 else None
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
-    kernel_ms = {n: [] for n in SCENES}
 
-    def step(record=False):
+    def step():
         for name in SCENES:
             if sharded is None:
                 ctx.render_into(frames[name].data_ptr(), H, W, prepared[name], spp=SPP)
-                if record:
-                    kernel_ms[name].append(None)  # filled after sync (events are per context: read per frame)
             else:
                 sharded.render(H, W, prepared[name], spp=SPP)
 
@@ -284,6 +281,22 @@ def run_ours(args):
                 "algorithmic_bytes_per_launch": {n: alg_bytes[n] for n in SCENES}, "per_scene": per_scene,
                 "note": "algorithmic bytes = 32 B x box tests + 16 B x sphere tests of the REFERENCE traversal + 4 B x pixels; "
                         "the scene (<1 MB) is shared-memory/L2 resident, so real DRAM traffic is far below this (see profiles/)"}
+
+    # N > 1 diagnostic: this rank's render-kernel time per frame (shard only, no gather), to separate kernel scaling
+    # from collective / synchronisation cost
+    rank_kernel_ms = None
+    if world > 1:
+        mine = {}
+        for name in SCENES:
+            ms = []
+            for _ in range(5):
+                ctx.render_shard_into(sharded._tiles.data_ptr(), H, W, prepared[name], spp=SPP)
+                torch.cuda.synchronize()
+                ms.append(ctx.last_render_ms())
+            mine[name] = round(sorted(ms)[2], 3)
+        allv = [None] * world
+        dist.all_gather_object(allv, mine)
+        rank_kernel_ms = {n: [v[n] for v in allv] for n in SCENES}
 
     # e2e: host buffers through the public API, H2D + render + D2H inside the timed region (wall clock)
     e2e = None
@@ -384,7 +397,7 @@ def run_ours(args):
                        "parallelism": f"tile-sharded x{world}, one NCCL gather per frame" if world > 1 else "single GPU",
                        "ray": "one ray segment = one objs_hit call (ray.fut:76-86)"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-            "frame_ms_1spp": one_spp, "extra": extra,
+            "frame_ms_1spp": one_spp, "extra": extra, "shard_kernel_ms_per_rank": rank_kernel_ms,
             "published_reference_1spp_ms": {"futhark_multicore_ryzen1700x": {"rgbbox": 179, "irreg": 62},
                                             "futhark_gpu_mi100": {"rgbbox": 14, "irreg": 8}},
         }

@@ -118,6 +118,21 @@ def test_warpqueue_sample_spreading(R, oracle, tuning):
             np.testing.assert_array_equal(tiles.cpu().numpy(), D.extract_rank_tiles(want, rank, world))
 
 
+def test_warpqueue_deep_tree_and_many_samples(R, oracle):
+    """Deep tree (bigger per-warp stacks -> fewer warps fit) and a sample count larger than one ring round."""
+    n, h, w = 150000, 64, 96
+    want, _, _ = oracle.render_scene("random", h, w, n=n, seed=11)
+    with R.Context(kernel="warpqueue") as ctx:
+        pr = ctx.prepare_scene(h, w, ctx.scene_random(n, 11))
+        assert pr.info()["max_depth"] >= 20
+        assert_same(ctx.render_host(h, w, pr), want, "deep tree, 1 spp")
+    h, w, spp = 24, 40, 300
+    want, _, _ = oracle.Scene.irreg().prepare(h, w).render(h, w, spp=spp)
+    with R.Context(kernel="warpqueue") as ctx:
+        pr = ctx.prepare_scene(h, w, ctx.irreg())
+        assert_same(ctx.render_host(h, w, pr, spp=spp), want, "300 spp, spread")
+
+
 def test_headline_config_64spp_kernels_agree(R):
     """BASELINE configs[1]/[2] (1000x1000, 64 spp): too slow for the CPU oracle inside a test, so the kernels
     (lane-bound K1, sample-spread K3, pixel-bound K3) are checked against each other bit-for-bit."""
