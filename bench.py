@@ -132,6 +132,9 @@ def cpu_sample(threads=0):
     """Times the oracle on rows j % ROW_STEP == 0 of both headline frames at SPP.  Returns
     (segments, seconds, cores)."""
     from oracle import pyoracle as O
+    if threads <= 0:  # all host threads the container may actually run: the cgroup CPU quota when there is one
+        q = host_cpu_quota()
+        threads = max(1, int(q + 0.5)) if q else 0
     cores = O.num_procs() if threads <= 0 else threads
     segs, secs = 0, 0.0
     for name in SCENES:

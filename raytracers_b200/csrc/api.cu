@@ -26,7 +26,7 @@ struct futhark_context_config {
   int32_t spp = 1;
   int32_t kernel = RAY_B200_KERNEL_AUTO;
   int32_t rank = 0, world = 1;
-  int32_t block_threads = 256, blocks_per_sm = 4, smem_budget = 48 * 1024, refill_min = 8, tail_from = 8;
+  int32_t blocks_per_sm = 4, smem_budget = 48 * 1024, refill_min = 8, tail_from = 8;
   int32_t wq_warps = 24, wq_k = 1, wq_spread = 1, permute = 1, host_build = 0;
   std::string cache_file;
 };
@@ -53,7 +53,6 @@ struct futhark_context {
   float4 *sample_buf = nullptr;             // warp-queue kernel, spp > 1: per-warp finished-sample colours
   size_t sample_buf_bytes = 0;
   bool profiling_paused = false;
-  double total_render_ms = 0.0;
   int64_t renders = 0;
   bool ok = false;
 };
@@ -150,7 +149,11 @@ int resolve_kernel(const futhark_context *ctx);
 int fill_params(futhark_context *ctx, const futhark_opaque_prepared_scene *p, int64_t h, int64_t w, int32_t spp,
                 int32_t rank, int32_t world, int32_t *out_pix, float *out_rgb, bool tile_major, RenderParams &P) {
   if (!p || !p->dev.nodes) { set_error(ctx, "render: invalid prepared scene"); return 1; }
-  if (h <= 0 || w <= 0 || h > 65536 || w > 65536) { set_error(ctx, "render: bad image size %lldx%lld", (long long)h, (long long)w); return 1; }
+  if (h <= 0 || w <= 0 || h > 65536 || w > 65536 || ((h + 3) / 4) * ((w + 7) / 8) > ((int64_t)1 << 25)) {
+    // work items are 32-bit: at most 2^30 (padded) pixels per frame
+    set_error(ctx, "render: bad image size %lldx%lld", (long long)h, (long long)w);
+    return 1;
+  }
   if (spp < 1) { set_error(ctx, "render: spp must be >= 1"); return 1; }
   if (world < 1 || rank < 0 || rank >= world) { set_error(ctx, "render: bad shard %d/%d", rank, world); return 1; }
   if (p->max_depth > kStackSize - 1) { set_error(ctx, "render: BVH depth %d exceeds the traversal stack", p->max_depth); return 1; }
@@ -244,7 +247,6 @@ int ensure_wavefront(futhark_context *ctx, int64_t items) {
 int do_render(futhark_context *ctx, RenderParams &P) {
   LaunchConfig lc;
   lc.kernel = resolve_kernel(ctx);
-  lc.block_threads = ctx->cfg.block_threads;
   lc.blocks_per_sm = ctx->cfg.blocks_per_sm;
   lc.sm_count = ctx->sm_count;
   lc.smem_budget = ctx->cfg.smem_budget;

@@ -57,7 +57,6 @@ struct WavefrontBuffers {
 
 struct LaunchConfig {
   int kernel;          // ray_b200_kernel
-  int block_threads;   // persistent/wavefront CTA size
   int blocks_per_sm;
   int sm_count;
   int smem_budget;     // bytes of dynamic shared memory per CTA for BVH staging
