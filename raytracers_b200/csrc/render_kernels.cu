@@ -515,7 +515,8 @@ constexpr uint32_t kIndexMask = (1u << kSlotShift) - 1u;
 constexpr unsigned long long kNoHit = ~0ull;
 
 template <int K, bool kSpread, bool kAllNodes, bool kSpheres>
-__global__ void __launch_bounds__(768, 1) render_warpqueue_kernel(const __grid_constant__ RenderParams P, const int ncap) {
+__global__ void __launch_bounds__(768, 1) render_warpqueue_kernel(const __grid_constant__ RenderParams P, const int ncap,
+                                                                   const int packet_min) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const float4 *s_nodes, *s_geom;
   stage_scene(P, smem_raw, s_nodes, s_geom);
@@ -535,7 +536,9 @@ __global__ void __launch_bounds__(768, 1) render_warpqueue_kernel(const __grid_c
   int *p_item = reinterpret_cast<int *>(best + R);     // work item (pixel) of the slot, -1 = idle
   int *ring_item = p_item + R;                         // spread: pixel item of ring entry m
   int *ring_done = ring_item + kWqRing;                // spread: samples finished, -1 = entry free
-  uint32_t *lstk = reinterpret_cast<uint32_t *>(ring_done + kWqRing);
+  int *pk_node = ring_done + kWqRing;                  // packet walk: deferred (node, lane mask) pairs, warp-uniform
+  unsigned *pk_mask = reinterpret_cast<unsigned *>(pk_node + kWqPacketStack);
+  uint32_t *lstk = reinterpret_cast<uint32_t *>(pk_mask + kWqPacketStack);
   uint32_t *nstk = lstk + kWqLeafStack;
 
   const int total = (int)(P.local_tiles * kTilePixels);
@@ -603,6 +606,9 @@ __global__ void __launch_bounds__(768, 1) render_warpqueue_kernel(const __grid_c
 
   for (;;) {
     unsigned trav = 0;  // bit k: slot lane+32k has a traversal in flight this round
+    unsigned gomask[K];  // warp-uniform: lanes whose slot lane+32k starts a traversal this round
+#pragma unroll
+    for (int k = 0; k < K; k++) gomask[k] = 0u;
     for (int pass = 0; pass < 4; pass++) {
       // ---------------------------------------------------------------- hand work to idle slots
       if (kSpread) finalize_pixels();
@@ -719,11 +725,8 @@ __global__ void __launch_bounds__(768, 1) render_warpqueue_kernel(const __grid_c
           }
         }
         const unsigned m = __ballot_sync(kFullMask, go);
-        if (go) {
-          nstk[ntop + __popc(m & lt_mask)] = (uint32_t)slot << kSlotShift;  // (slot, root node 0)
-          trav |= 1u << k;
-        }
-        ntop += __popc(m);
+        if (go) trav |= 1u << k;
+        gomask[k] |= m;  // the traversal of these rays starts at the root after the passes
       }
       // another pass only helps if some slot is idle and there is still work to hand out
       bool idle_left = false;
@@ -733,7 +736,10 @@ __global__ void __launch_bounds__(768, 1) render_warpqueue_kernel(const __grid_c
       if (!more || !__any_sync(kFullMask, idle_left)) break;
     }
     __syncwarp();
-    if (ntop == 0) {
+    unsigned any_go = 0u;
+#pragma unroll
+    for (int k = 0; k < K; k++) any_go |= gomask[k];
+    if (any_go == 0u) {
       bool any_active = false;
 #pragma unroll
       for (int k = 0; k < K; k++) any_active |= p_item[lane + 32 * k] >= 0;
@@ -765,10 +771,10 @@ __global__ void __launch_bounds__(768, 1) render_warpqueue_kernel(const __grid_c
       }
       ltop -= n;
     };
-    auto node_batch = [&](auto full_tag) {
+    auto node_batch = [&](auto full_tag, const int n_part) {
       // one BVH2C node step (both children's boxes) for up to 32 (ray, node) pairs
       constexpr bool kFull = decltype(full_tag)::value;
-      const int n = kFull ? 32 : ntop;
+      const int n = kFull ? 32 : n_part;
       bool pl_node = false, pr_node = false, pl_leaf = false, pr_leaf = false;
       uint32_t tag = 0;
       int lptr = 0, rptr = 0;
@@ -809,13 +815,102 @@ __global__ void __launch_bounds__(768, 1) render_warpqueue_kernel(const __grid_c
     };
     using full_t = std::integral_constant<bool, true>;
     using part_t = std::integral_constant<bool, false>;
-    while (ntop > 0 || ltop > 0) {
-      if (ltop >= 32) leaf_batch(full_t{});
-      else if (ntop >= 32) node_batch(full_t{});
-      else if (ntop > 0) node_batch(part_t{});
-      else leaf_batch(part_t{});
+    // Runs the item queues dry.  Without packet spills the depth-sorted LIFO never exceeds the proved bound; with
+    // spills (arbitrary depths) a guard keeps it safe for ANY content: once fewer than 96 entries are free, items are
+    // taken one at a time, a plain DFS that can add at most (tree depth) < 64 entries before it shrinks again.
+    auto drain = [&]() {
       __syncwarp();
+      while (ntop > 0 || ltop > 0) {
+        const bool tight = ntop + 96 > ncap;
+        if (ltop >= 32) leaf_batch(full_t{});
+        else if (ntop >= 32 && !tight) node_batch(full_t{}, 32);
+        else if (ntop > 0) node_batch(part_t{}, tight ? 1 : ntop);
+        else leaf_batch(part_t{});
+        __syncwarp();
+      }
+    };
+    // Packet walk.  Near the root almost every ray of a warp visits the same nodes, so those node steps are done the
+    // cheap way: ONE (node, lane mask) pair for the whole warp, the node fetched once (same address in every lane =
+    // a shared-memory broadcast), each lane testing its own slot's ray, leaf children tested inline by the owner lanes
+    // (plain read-modify-write of their own `best` word).  As soon as fewer than `packet_min` lanes are left on a node
+    // the remaining (ray, node) pairs are handed to the item queue, where lanes are bound to items instead of rays.
+    auto packet_walk = [&](const int k, unsigned mask) {
+      const int slot = lane + 32 * k;
+      int cur = 0, psp = 0;
+      for (;;) {
+        const int cnt = __popc(mask);
+        bool descended = false;
+        if (cnt < packet_min) {
+          if (cnt) {
+            if (ntop + 32 + 96 > ncap) drain();
+            if ((mask >> lane) & 1u) nstk[ntop + __popc(mask & lt_mask)] = ((uint32_t)slot << kSlotShift) | (uint32_t)cur;
+            ntop += cnt;
+          }
+        } else {
+          const bool in = (mask >> lane) & 1u;
+          float4 q0, q1, q2, q3;
+          sc.node(cur, q0, q1, q2, q3);
+          const int lptr = __float_as_int(q0.w), rptr = __float_as_int(q1.w);  // same node in every lane
+          bool hl = false, hr = false;
+          if (in) {
+            const float4 ro = ray_o[slot], ri = ray_i[slot];
+            Ray r;
+            r.o = v3(ro.x, ro.y, ro.z);
+            RayInv q;
+            q.ix = ri.x; q.iy = ri.y; q.iz = ri.z; q.a = ro.w;
+            r.d = v3(0.0f, 0.0f, 0.0f);
+            hl = box_hit(q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, r, q);
+            hr = box_hit(q2.x, q2.y, q2.z, q3.x, q3.y, q3.z, r, q);
+            if (lptr < 0 || rptr < 0) {  // leaf children: visited by every ray that visits this node (bvh.fut:84)
+              const float4 rd = ray_d[slot];
+              r.d = v3(rd.x, rd.y, rd.z);
+              unsigned long long b = best[slot];
+              if (lptr < 0) {
+                const float4 g = sc.sphere(~lptr);
+                const float t = sphere_t(g.x, g.y, g.z, g.w, r, ro.w, 0.1f, 1000000000.0f);
+                const unsigned long long key = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)(~lptr);
+                if (t >= 0.0f && key < b) b = key;
+              }
+              if (rptr < 0) {
+                const float4 g = sc.sphere(~rptr);
+                const float t = sphere_t(g.x, g.y, g.z, g.w, r, ro.w, 0.1f, 1000000000.0f);
+                const unsigned long long key = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)(~rptr);
+                if (t >= 0.0f && key < b) b = key;
+              }
+              best[slot] = b;
+            }
+          }
+          const unsigned bl = lptr >= 0 ? __ballot_sync(kFullMask, hl) : 0u;
+          const unsigned br = rptr >= 0 ? __ballot_sync(kFullMask, hr) : 0u;
+          if (bl) {
+            if (br) {
+              if (lane == 0) { pk_node[psp] = rptr; pk_mask[psp] = br; }
+              psp++;
+            }
+            cur = lptr; mask = bl; descended = true;
+          } else if (br) {
+            cur = rptr; mask = br; descended = true;
+          }
+        }
+        if (descended) continue;
+        if (psp == 0) break;
+        psp--;
+        __syncwarp();
+        cur = pk_node[psp];
+        mask = pk_mask[psp];
+      }
+    };
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      if (packet_min > 0) {
+        if (gomask[k]) packet_walk(k, gomask[k]);
+      } else {
+        const bool go = (gomask[k] >> lane) & 1u;
+        if (go) nstk[ntop + __popc(gomask[k] & lt_mask)] = (uint32_t)(lane + 32 * k) << kSlotShift;  // (slot, root node 0)
+        ntop += __popc(gomask[k]);
+      }
     }
+    drain();
 
     // ---------------------------------------------------------------- shade: owner lanes finish the segment
 #pragma unroll
@@ -923,7 +1018,7 @@ void launch_render(const RenderParams &p, const LaunchConfig &lc, const Wavefron
     long long ctas = lc.sm_count;
     const long long useful = (items + 32 * k * lc.wq_warps - 1) / (32 * k * lc.wq_warps);
     if (ctas > useful) ctas = useful;
-#define RAYB200_WQ(KK, SP, A, S) render_warpqueue_kernel<KK, SP, A, S><<<(unsigned)ctas, wthreads, wsmem, stream>>>(p, ncap)
+#define RAYB200_WQ(KK, SP, A, S) render_warpqueue_kernel<KK, SP, A, S><<<(unsigned)ctas, wthreads, wsmem, stream>>>(p, ncap, lc.wq_packet)
 #define RAYB200_WQ2(KK, SP)                                                               \
   do {                                                                                    \
     if (all_nodes && sph) RAYB200_WQ(KK, SP, true, true);                                 \

@@ -64,6 +64,7 @@ struct LaunchConfig {
   int tail_from;       // wavefront: see WavefrontBuffers
   int wq_warps;        // warp-queue kernel: warps per CTA (one CTA per SM)
   int wq_k;            // warp-queue kernel: rays in flight per warp = 32 * wq_k (1 or 2)
+  int wq_packet;       // warp-queue kernel: node steps with at least this many lanes are done packet-style (0 = never)
 };
 
 void launch_render(const RenderParams &p, const LaunchConfig &lc, const WavefrontBuffers *wf, cudaStream_t stream,
@@ -77,11 +78,15 @@ __host__ __device__ inline size_t staging_bytes(const RenderParams &p) {
 }
 constexpr int kWqRing = 8;         // warp-queue kernel: pixels a warp may have open at once when samples are spread
 constexpr int kWqLeafStack = 128;  // warp-queue kernel: leaf-item stack (never more than 31 + 64 live)
+constexpr int kWqPacketStack = 64; // warp-queue kernel: deferred (node, mask) pairs of the packet walk (<= tree depth)
 // warp-queue kernel: node-stack capacity (proved bound, see render_kernels.cu) and per-warp / per-CTA bytes
-__host__ __device__ inline int wq_node_capacity(int k, int max_depth) { return 32 * k + 64 * (max_depth + 1); }
+__host__ __device__ inline int wq_node_capacity(int k, int max_depth) {
+  const int c = 32 * k + 64 * (max_depth + 1);
+  return c < 256 ? 256 : c;  // room for the overflow guard of the drain loop (96 free entries) on tiny trees
+}
 __host__ __device__ inline size_t wq_warp_bytes(int k, int ncap) {
   const size_t r = 32 * (size_t)k;
-  return ((r * (16 * 5 + 8 + 4) + 2 * kWqRing * 4 + kWqLeafStack * 4 + (size_t)ncap * 4) + 127) & ~(size_t)127;
+  return ((r * (16 * 5 + 8 + 4) + 2 * kWqRing * 4 + 2 * kWqPacketStack * 4 + kWqLeafStack * 4 + (size_t)ncap * 4) + 127) & ~(size_t)127;
 }
 cudaError_t configure_kernels(int max_dynamic_smem);
 

@@ -118,6 +118,26 @@ def test_warpqueue_sample_spreading(R, oracle, tuning):
             np.testing.assert_array_equal(tiles.cpu().numpy(), D.extract_rank_tiles(want, rank, world))
 
 
+@pytest.mark.parametrize("packet_min", [1, 8, 16, 32])
+def test_warpqueue_packet_walk(R, oracle, golden, packet_min):
+    """Packet steps for the dense top of the tree (wq_packet = lane threshold): same frames, bit for bit —
+    reference PNG, partial tiles, spp > 1, a deep random tree (spills at arbitrary depths, drain guard), K = 2."""
+    want, _ = golden["rgbbox_500"]
+    assert_same(gpu_frame(R, "rgbbox", 500, 500, "warpqueue", wq_packet=packet_min), want, f"packet {packet_min} vs reference PNG")
+    want, _ = golden["irreg_500"]
+    assert_same(gpu_frame(R, "irreg", 500, 500, "warpqueue", wq_packet=packet_min, wq_k=2, wq_warps=12), want, f"packet {packet_min} K=2")
+    w2, _, _ = oracle.Scene.rgbbox().prepare(45, 83).render(45, 83, spp=5)
+    assert_same(gpu_frame(R, "rgbbox", 45, 83, "warpqueue", spp=5, wq_packet=packet_min), w2, f"packet {packet_min} spp 5")
+    w3, _, _ = oracle.render_scene("random", 64, 96, n=60000, seed=3)
+    assert_same(gpu_frame(R, "random", 64, 96, "warpqueue", n=60000, seed=3, wq_packet=packet_min), w3, f"packet {packet_min} deep tree")
+    two = np.float32([[0, 0, 0, 1, 0, 0, 2], [3, 1, -4, 0, 1, 0, 3]])
+    cam = np.float32([0, 0, 20, 0, 0, 0, 60])
+    w4, _, _ = oracle.Scene.custom(two, cam).prepare(32, 48).render(32, 48)
+    with R.Context(kernel="warpqueue", wq_packet=packet_min) as ctx:
+        pr = ctx.prepare_scene(32, 48, ctx.scene_from_arrays(two, cam))
+        assert_same(ctx.render_host(32, 48, pr), w4, f"packet {packet_min} two spheres")
+
+
 def test_warpqueue_deep_tree_and_many_samples(R, oracle):
     """Deep tree (bigger per-warp stacks -> fewer warps fit) and a sample count larger than one ring round."""
     n, h, w = 150000, 64, 96
