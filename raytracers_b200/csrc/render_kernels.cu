@@ -884,6 +884,7 @@ __global__ void __launch_bounds__(768, 1) render_warpqueue_kernel(const __grid_c
           const unsigned br = rptr >= 0 ? __ballot_sync(kFullMask, hr) : 0u;
           if (bl) {
             if (br) {
+              __syncwarp();  // every lane is done reading the entry this may overwrite
               if (lane == 0) { pk_node[psp] = rptr; pk_mask[psp] = br; }
               psp++;
             }

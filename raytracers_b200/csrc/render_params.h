@@ -81,8 +81,11 @@ constexpr int kWqLeafStack = 128;  // warp-queue kernel: leaf-item stack (never 
 constexpr int kWqPacketStack = 64; // warp-queue kernel: deferred (node, mask) pairs of the packet walk (<= tree depth)
 // warp-queue kernel: node-stack capacity (proved bound, see render_kernels.cu) and per-warp / per-CTA bytes
 __host__ __device__ inline int wq_node_capacity(int k, int max_depth) {
+  // 32k + 64(depth+1) is the proved bound of the depth-sorted LIFO; the drain loop's overflow guard makes ANY capacity
+  // >= 256 safe (it falls back to one-item-at-a-time DFS when fewer than 96 entries are free), so deep trees are
+  // capped at 1024 entries instead of costing warps or staging space
   const int c = 32 * k + 64 * (max_depth + 1);
-  return c < 256 ? 256 : c;  // room for the overflow guard of the drain loop (96 free entries) on tiny trees
+  return c < 256 ? 256 : (c > 1024 ? 1024 : c);
 }
 __host__ __device__ inline size_t wq_warp_bytes(int k, int ncap) {
   const size_t r = 32 * (size_t)k;
