@@ -516,7 +516,7 @@ constexpr unsigned long long kNoHit = ~0ull;
 
 template <int K, bool kSpread, bool kAllNodes, bool kSpheres>
 __global__ void __launch_bounds__(768, 1) render_warpqueue_kernel(const __grid_constant__ RenderParams P, const int ncap,
-                                                                   const int packet_min) {
+                                                                   const int packet_min, const int refill_min) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const float4 *s_nodes, *s_geom;
   stage_scene(P, smem_raw, s_nodes, s_geom);
@@ -651,7 +651,8 @@ __global__ void __launch_bounds__(768, 1) render_warpqueue_kernel(const __grid_c
           }
           exhausted = base + cnt >= total_claims;
         }
-      } else if (cnt) {
+      } else if (cnt >= refill_min || cnt == R) {
+        // (refill_min > 1: wait until several slots are idle, so they get CONSECUTIVE samples and start as a coherent group)
         int avail = (open_seq - disp_seq) * spp - disp_s;
         while (!exhausted && avail < cnt) {  // open more pixels (one cursor claim each) while the ring has room
           const int m = open_seq & (kWqRing - 1);
@@ -1019,7 +1020,7 @@ void launch_render(const RenderParams &p, const LaunchConfig &lc, const Wavefron
     long long ctas = lc.sm_count;
     const long long useful = (items + 32 * k * lc.wq_warps - 1) / (32 * k * lc.wq_warps);
     if (ctas > useful) ctas = useful;
-#define RAYB200_WQ(KK, SP, A, S) render_warpqueue_kernel<KK, SP, A, S><<<(unsigned)ctas, wthreads, wsmem, stream>>>(p, ncap, lc.wq_packet)
+#define RAYB200_WQ(KK, SP, A, S) render_warpqueue_kernel<KK, SP, A, S><<<(unsigned)ctas, wthreads, wsmem, stream>>>(p, ncap, lc.wq_packet, lc.wq_refill)
 #define RAYB200_WQ2(KK, SP)                                                               \
   do {                                                                                    \
     if (all_nodes && sph) RAYB200_WQ(KK, SP, true, true);                                 \

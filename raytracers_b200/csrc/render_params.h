@@ -64,6 +64,7 @@ struct LaunchConfig {
   int tail_from;       // wavefront: see WavefrontBuffers
   int wq_warps;        // warp-queue kernel: warps per CTA (one CTA per SM)
   int wq_k;            // warp-queue kernel: rays in flight per warp = 32 * wq_k (1 or 2)
+  int wq_refill;       // warp-queue kernel, spread mode: hand out samples when at least this many slots are idle
   int wq_packet;       // warp-queue kernel: node steps with at least this many lanes are done packet-style (0 = never)
 };
 
