@@ -27,7 +27,7 @@ struct futhark_context_config {
   int32_t kernel = RAY_B200_KERNEL_AUTO;
   int32_t rank = 0, world = 1;
   int32_t blocks_per_sm = 4, smem_budget = 48 * 1024, refill_min = 8, tail_from = 8;
-  int32_t wq_warps = 24, wq_k = 1, wq_spread = 1, wq_packet = -1, wq_refill = 1, wq_chain = 0, permute = 1, host_build = 0;
+  int32_t wq_warps = 24, wq_k = 1, wq_spread = 1, wq_packet = -1, wq_refill = 1, permute = 1, host_build = 0;
   std::string cache_file;
 };
 
@@ -120,7 +120,7 @@ int parse_kernel(const char *v, int dflt) {
   return atoi(v);
 }
 
-const char *kTuningNames[] = {"kernel", "spp", "blocks_per_sm", "smem_budget", "refill_min", "tail_from", "wq_warps", "wq_k", "wq_spread", "wq_packet", "wq_refill", "wq_chain", "permute", "host_build", "rank", "world"};
+const char *kTuningNames[] = {"kernel", "spp", "blocks_per_sm", "smem_budget", "refill_min", "tail_from", "wq_warps", "wq_k", "wq_spread", "wq_packet", "wq_refill", "permute", "host_build", "rank", "world"};
 constexpr int kNumTuning = sizeof(kTuningNames) / sizeof(kTuningNames[0]);
 
 bool bad_ctx(futhark_context *ctx) { return ctx == nullptr || !ctx->ok; }
@@ -254,7 +254,6 @@ int do_render(futhark_context *ctx, RenderParams &P) {
   lc.tail_from = ctx->cfg.tail_from;
   lc.wq_warps = ctx->plan_wq_warps > 0 ? ctx->plan_wq_warps : 1;
   lc.wq_k = ctx->cfg.wq_k == 1 ? 1 : 2;
-  lc.wq_chain = ctx->cfg.wq_chain < 0 ? 0 : (ctx->cfg.wq_chain > 8 ? 8 : ctx->cfg.wq_chain);
   lc.wq_refill = ctx->cfg.wq_refill < 1 ? 1 : (ctx->cfg.wq_refill > 32 ? 32 : ctx->cfg.wq_refill);
   // packet steps pay off when item-mode node fetches are expensive, i.e. when part of the tree is not staged in
   // shared memory (measured: irreg -19 %, rgbbox +1..2 %); -1 = decide per scene
@@ -428,7 +427,6 @@ int futhark_context_config_set_tuning_param(struct futhark_context_config *cfg, 
   else if (!strcmp(name, "wq_k")) cfg->wq_k = (int32_t)v;
   else if (!strcmp(name, "wq_spread")) cfg->wq_spread = (int32_t)v;
   else if (!strcmp(name, "wq_refill")) cfg->wq_refill = (int32_t)v;
-  else if (!strcmp(name, "wq_chain")) cfg->wq_chain = (int32_t)v;
   else if (!strcmp(name, "wq_packet")) cfg->wq_packet = (int32_t)v;  // (size_t)-1 = decide per scene
   else if (!strcmp(name, "permute")) cfg->permute = (int32_t)v;
   else if (!strcmp(name, "host_build")) cfg->host_build = (int32_t)v;
@@ -457,7 +455,6 @@ struct futhark_context *futhark_context_new(struct futhark_context_config *cfg) 
   ctx->cfg.wq_spread = env_int("RAY_WQ_SPREAD", ctx->cfg.wq_spread);
   ctx->cfg.wq_packet = env_int("RAY_WQ_PACKET", ctx->cfg.wq_packet);
   ctx->cfg.wq_refill = env_int("RAY_WQ_REFILL", ctx->cfg.wq_refill);
-  ctx->cfg.wq_chain = env_int("RAY_WQ_CHAIN", ctx->cfg.wq_chain);
   ctx->cfg.permute = env_int("RAY_PERMUTE", ctx->cfg.permute);
   ctx->cfg.host_build = env_int("RAY_HOST_BUILD", ctx->cfg.host_build);
   memset(&ctx->wf, 0, sizeof ctx->wf);

@@ -516,7 +516,7 @@ constexpr unsigned long long kNoHit = ~0ull;
 
 template <int K, bool kSpread, bool kAllNodes, bool kSpheres>
 __global__ void __launch_bounds__(768, 1) render_warpqueue_kernel(const __grid_constant__ RenderParams P, const int ncap,
-                                                                   const int packet_min, const int refill_min, const int chain_max) {
+                                                                   const int packet_min, const int refill_min) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const float4 *s_nodes, *s_geom;
   stage_scene(P, smem_raw, s_nodes, s_geom);
@@ -793,18 +793,8 @@ __global__ void __launch_bounds__(768, 1) render_warpqueue_kernel(const __grid_c
         q.ix = ri.x; q.iy = ri.y; q.iz = ri.z; q.a = ro.w;
         lptr = __float_as_int(q0.w);
         rptr = __float_as_int(q1.w);
-        bool hl = box_hit(q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, r, q);
-        bool hr = box_hit(q2.x, q2.y, q2.z, q3.x, q3.y, q3.z, r, q);
-        // Chain following: when both children are inner nodes and exactly one of them is hit there is nothing to
-        // push, so the lane steps straight into that child instead of sending it through the queue (up to
-        // `chain_max` times; the other lanes idle meanwhile, which is still cheaper than a queue round trip).
-        for (int c = 0; c < chain_max && lptr >= 0 && rptr >= 0 && (hl != hr); c++) {
-          sc.node(hl ? lptr : rptr, q0, q1, q2, q3);
-          lptr = __float_as_int(q0.w);
-          rptr = __float_as_int(q1.w);
-          hl = box_hit(q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, r, q);
-          hr = box_hit(q2.x, q2.y, q2.z, q3.x, q3.y, q3.z, r, q);
-        }
+        const bool hl = box_hit(q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, r, q);
+        const bool hr = box_hit(q2.x, q2.y, q2.z, q3.x, q3.y, q3.z, r, q);
         pl_leaf = lptr < 0;          // a leaf child has no box in the reference: always visited
         pr_leaf = rptr < 0;
         pl_node = hl && !pl_leaf;
@@ -1030,7 +1020,7 @@ void launch_render(const RenderParams &p, const LaunchConfig &lc, const Wavefron
     long long ctas = lc.sm_count;
     const long long useful = (items + 32 * k * lc.wq_warps - 1) / (32 * k * lc.wq_warps);
     if (ctas > useful) ctas = useful;
-#define RAYB200_WQ(KK, SP, A, S) render_warpqueue_kernel<KK, SP, A, S><<<(unsigned)ctas, wthreads, wsmem, stream>>>(p, ncap, lc.wq_packet, lc.wq_refill, lc.wq_chain)
+#define RAYB200_WQ(KK, SP, A, S) render_warpqueue_kernel<KK, SP, A, S><<<(unsigned)ctas, wthreads, wsmem, stream>>>(p, ncap, lc.wq_packet, lc.wq_refill)
 #define RAYB200_WQ2(KK, SP)                                                               \
   do {                                                                                    \
     if (all_nodes && sph) RAYB200_WQ(KK, SP, true, true);                                 \

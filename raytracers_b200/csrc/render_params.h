@@ -65,7 +65,6 @@ struct LaunchConfig {
   int wq_warps;        // warp-queue kernel: warps per CTA (one CTA per SM)
   int wq_k;            // warp-queue kernel: rays in flight per warp = 32 * wq_k (1 or 2)
   int wq_refill;       // warp-queue kernel, spread mode: hand out samples when at least this many slots are idle
-  int wq_chain;        // warp-queue kernel: max single-child steps a lane takes in place before going back to the queue
   int wq_packet;       // warp-queue kernel: node steps with at least this many lanes are done packet-style (0 = never)
 };
 

@@ -138,19 +138,6 @@ def test_warpqueue_packet_walk(R, oracle, golden, packet_min):
         assert_same(ctx.render_host(32, 48, pr), w4, f"packet {packet_min} two spheres")
 
 
-@pytest.mark.parametrize("chain", [1, 2, 4])
-def test_warpqueue_chain_following(R, oracle, golden, chain):
-    """Lanes that hit exactly one inner child step into it in place (wq_chain): same frames bit for bit."""
-    want, _ = golden["rgbbox_500"]
-    assert_same(gpu_frame(R, "rgbbox", 500, 500, "warpqueue", wq_chain=chain), want, f"chain {chain} rgbbox")
-    want, _ = golden["irreg_500"]
-    assert_same(gpu_frame(R, "irreg", 500, 500, "warpqueue", wq_chain=chain), want, f"chain {chain} irreg (packet auto)")
-    w3, _, _ = oracle.render_scene("random", 64, 96, n=60000, seed=3)
-    assert_same(gpu_frame(R, "random", 64, 96, "warpqueue", n=60000, seed=3, wq_chain=chain, wq_packet=0), w3, f"chain {chain} deep tree")
-    w2, _, _ = oracle.Scene.rgbbox().prepare(45, 83).render(45, 83, spp=5)
-    assert_same(gpu_frame(R, "rgbbox", 45, 83, "warpqueue", spp=5, wq_chain=chain), w2, f"chain {chain} spp 5")
-
-
 def test_warpqueue_deep_tree_and_many_samples(R, oracle):
     """Deep tree (bigger per-warp stacks -> fewer warps fit) and a sample count larger than one ring round."""
     n, h, w = 150000, 64, 96
