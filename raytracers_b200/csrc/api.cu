@@ -49,7 +49,7 @@ struct futhark_context {
   struct PinnedBlock { unsigned char *ptr; size_t bytes; cudaEvent_t last_use; };
   std::vector<PinnedBlock> pinned_cache;    // page-locked upload buffers of freed prepared scenes, reused by the next prepare_scene
   BvhBuildResult *d_build_result = nullptr, *h_build_result = nullptr;  // device scratch / page-locked host mirror
-  int32_t plan_wq_warps = 0;                // warps per CTA the warp-queue kernel will use for the frame being set up
+  int32_t plan_wq_warps = 0, plan_wq_packet = 0;                // warps per CTA the warp-queue kernel will use for the frame being set up
   float4 *sample_buf = nullptr;             // warp-queue kernel, spp > 1: per-warp finished-sample colours
   size_t sample_buf_bytes = 0;
   bool profiling_paused = false;
@@ -191,11 +191,27 @@ int fill_params(futhark_context *ctx, const futhark_opaque_prepared_scene *p, in
     // one CTA per SM: as many warps as asked for (<= 24) while their queues leave >= 8 KB for staging;
     // deep trees need bigger node stacks, so they get fewer warps
     const int k = ctx->cfg.wq_k == 1 ? 1 : 2;
-    const int64_t per_warp = (int64_t)wq_warp_bytes(k, wq_node_capacity(k, p->max_depth));
-    int64_t wq_w = ctx->cfg.wq_warps < 1 ? 1 : (ctx->cfg.wq_warps > 24 ? 24 : ctx->cfg.wq_warps);
-    while (wq_w > 1 && wq_w * per_warp + 8192 > (int64_t)ctx->max_smem_optin) wq_w--;
+    // Packet steps pay off when item-mode node fetches are expensive (part of the tree not staged in shared memory)
+    // AND the rays a warp holds are coherent: samples of one pixel (spp > 1) or primary rays of a dense frame.
+    // Measured: irreg 64 spp -19 %, irreg 4000^2 1 spp -12 %; rgbbox (fully staged) +1..2 %; 1000^2 1 spp +5 %.
+    // The plan is made twice: first assuming packets, to see whether the tree would be fully staged anyway.
+    int want_packet = ctx->cfg.wq_packet;
+    const bool coherent = spp > 1 || h * w >= ((int64_t)1 << 22);
+    int64_t per_warp = 0, wq_w = 0;
+    for (int attempt = 0; attempt < 2; attempt++) {
+      const bool pk = want_packet != 0;
+      per_warp = (int64_t)wq_warp_bytes(k, wq_node_capacity(k, p->max_depth), pk);
+      wq_w = ctx->cfg.wq_warps < 1 ? 1 : (ctx->cfg.wq_warps > 24 ? 24 : ctx->cfg.wq_warps);
+      while (wq_w > 1 && wq_w * per_warp + 8192 > (int64_t)ctx->max_smem_optin) wq_w--;
+      if (want_packet >= 0) break;
+      const int64_t b = (int64_t)ctx->max_smem_optin - wq_w * per_warp - 512 - 128;
+      const bool fully_staged = b / 64 >= (int64_t)(p->n - 1);
+      want_packet = (!fully_staged && coherent) ? 24 : 0;
+      if (want_packet != 0) break;  // the first plan (with packets) stands
+    }
     budget = (int64_t)ctx->max_smem_optin - wq_w * per_warp - 512;
     if (budget < 256) { set_error(ctx, "render: warp-queue kernel does not fit shared memory (tree depth %d)", p->max_depth); return 1; }
+    ctx->plan_wq_packet = want_packet > 32 ? 32 : want_packet;
     ctx->plan_wq_warps = (int32_t)wq_w;
   }
   int64_t nodes_fit = std::max<int64_t>(0, budget / 64);
@@ -255,9 +271,7 @@ int do_render(futhark_context *ctx, RenderParams &P) {
   lc.wq_warps = ctx->plan_wq_warps > 0 ? ctx->plan_wq_warps : 1;
   lc.wq_k = ctx->cfg.wq_k == 1 ? 1 : 2;
   lc.wq_refill = ctx->cfg.wq_refill < 1 ? 1 : (ctx->cfg.wq_refill > 32 ? 32 : ctx->cfg.wq_refill);
-  // packet steps pay off when item-mode node fetches are expensive, i.e. when part of the tree is not staged in
-  // shared memory (measured: irreg -19 %, rgbbox +1..2 %); -1 = decide per scene
-  lc.wq_packet = ctx->cfg.wq_packet < 0 ? (P.smem_nodes == P.n_inner ? 0 : 24) : (ctx->cfg.wq_packet > 32 ? 32 : ctx->cfg.wq_packet);
+  lc.wq_packet = ctx->plan_wq_packet;
   if (lc.kernel == RAY_B200_KERNEL_WAVEFRONT && ensure_wavefront(ctx, P.local_tiles * kTilePixels)) return 1;
   P.sample_buf = nullptr;
   if (lc.kernel == RAY_B200_KERNEL_WARPQUEUE && P.spp > 1 && P.spp <= 65535 && ctx->cfg.wq_spread) {

@@ -514,7 +514,7 @@ constexpr int kSlotShift = 26;                 // item = slot << 26 | index  (in
 constexpr uint32_t kIndexMask = (1u << kSlotShift) - 1u;
 constexpr unsigned long long kNoHit = ~0ull;
 
-template <int K, bool kSpread, bool kAllNodes, bool kSpheres>
+template <int K, bool kSpread, bool kPacket, bool kAllNodes, bool kSpheres>
 __global__ void __launch_bounds__(768, 1) render_warpqueue_kernel(const __grid_constant__ RenderParams P, const int ncap,
                                                                    const int packet_min, const int refill_min) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -526,7 +526,7 @@ __global__ void __launch_bounds__(768, 1) render_warpqueue_kernel(const __grid_c
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
   const unsigned gt_mask = lane == 31 ? 0u : ~((2u << lane) - 1u);
-  unsigned char *wbase = smem_raw + ((staging_bytes(P) + 127) & ~(size_t)127) + (size_t)warp * wq_warp_bytes(K, ncap);
+  unsigned char *wbase = smem_raw + ((staging_bytes(P) + 127) & ~(size_t)127) + (size_t)warp * wq_warp_bytes(K, ncap, kPacket);
   float4 *ray_o = reinterpret_cast<float4 *>(wbase);   // {o.xyz, a = dot d d}
   float4 *ray_i = ray_o + R;                           // {1/d.xyz, 0}
   float4 *ray_d = ray_i + R;                           // {d.xyz, 0}
@@ -538,7 +538,7 @@ __global__ void __launch_bounds__(768, 1) render_warpqueue_kernel(const __grid_c
   int *ring_done = ring_item + kWqRing;                // spread: samples finished, -1 = entry free
   int *pk_node = ring_done + kWqRing;                  // packet walk: deferred (node, lane mask) pairs, warp-uniform
   unsigned *pk_mask = reinterpret_cast<unsigned *>(pk_node + kWqPacketStack);
-  uint32_t *lstk = reinterpret_cast<uint32_t *>(pk_mask + kWqPacketStack);
+  uint32_t *lstk = reinterpret_cast<uint32_t *>(kPacket ? pk_mask + kWqPacketStack : reinterpret_cast<unsigned *>(pk_node));
   uint32_t *nstk = lstk + kWqLeafStack;
 
   const int total = (int)(P.local_tiles * kTilePixels);
@@ -835,7 +835,7 @@ __global__ void __launch_bounds__(768, 1) render_warpqueue_kernel(const __grid_c
     // a shared-memory broadcast), each lane testing its own slot's ray, leaf children tested inline by the owner lanes
     // (plain read-modify-write of their own `best` word).  As soon as fewer than `packet_min` lanes are left on a node
     // the remaining (ray, node) pairs are handed to the item queue, where lanes are bound to items instead of rays.
-    auto packet_walk = [&](const int k, unsigned mask) {
+    [[maybe_unused]] auto packet_walk = [&](const int k, unsigned mask) {
       const int slot = lane + 32 * k;
       int cur = 0, psp = 0;
       for (;;) {
@@ -904,8 +904,10 @@ __global__ void __launch_bounds__(768, 1) render_warpqueue_kernel(const __grid_c
     };
 #pragma unroll
     for (int k = 0; k < K; k++) {
-      if (packet_min > 0) {
-        if (gomask[k]) packet_walk(k, gomask[k]);
+      if (kPacket && packet_min > 0) {
+        if constexpr (kPacket) {
+          if (gomask[k]) packet_walk(k, gomask[k]);
+        }
       } else {
         const bool go = (gomask[k] >> lane) & 1u;
         if (go) nstk[ntop + __popc(gomask[k] & lt_mask)] = (uint32_t)(lane + 32 * k) << kSlotShift;  // (slot, root node 0)
@@ -969,12 +971,13 @@ cudaError_t configure_kernels(int max_dynamic_smem) {
   RAYB200_SET((wavefront_bounce_kernel<true, false>));
   RAYB200_SET((wavefront_bounce_kernel<false, true>));
   RAYB200_SET((wavefront_bounce_kernel<false, false>));
-#define RAYB200_SET_WQ(KK, SP)                                  \
-  RAYB200_SET((render_warpqueue_kernel<KK, SP, true, true>));   \
-  RAYB200_SET((render_warpqueue_kernel<KK, SP, true, false>));  \
-  RAYB200_SET((render_warpqueue_kernel<KK, SP, false, true>));  \
-  RAYB200_SET((render_warpqueue_kernel<KK, SP, false, false>));
-  RAYB200_SET_WQ(1, false) RAYB200_SET_WQ(1, true) RAYB200_SET_WQ(2, false) RAYB200_SET_WQ(2, true)
+#define RAYB200_SET_WQ(KK, SP, PK)                                  \
+  RAYB200_SET((render_warpqueue_kernel<KK, SP, PK, true, true>));   \
+  RAYB200_SET((render_warpqueue_kernel<KK, SP, PK, true, false>));  \
+  RAYB200_SET((render_warpqueue_kernel<KK, SP, PK, false, true>));  \
+  RAYB200_SET((render_warpqueue_kernel<KK, SP, PK, false, false>));
+  RAYB200_SET_WQ(1, false, false) RAYB200_SET_WQ(1, true, false) RAYB200_SET_WQ(2, false, false) RAYB200_SET_WQ(2, true, false)
+  RAYB200_SET_WQ(1, false, true) RAYB200_SET_WQ(1, true, true) RAYB200_SET_WQ(2, false, true) RAYB200_SET_WQ(2, true, true)
 #undef RAYB200_SET_WQ
 #undef RAYB200_SET
   return cudaSuccess;
@@ -1016,21 +1019,28 @@ void launch_render(const RenderParams &p, const LaunchConfig &lc, const Wavefron
     const int k = lc.wq_k == 1 ? 1 : 2;
     const int wthreads = 32 * lc.wq_warps;
     const int ncap = wq_node_capacity(k, p.max_depth);
-    const size_t wsmem = ((staging_bytes(p) + 127) & ~(size_t)127) + (size_t)lc.wq_warps * wq_warp_bytes(k, ncap);
+    const bool packet = lc.wq_packet > 0;
+    const size_t wsmem = ((staging_bytes(p) + 127) & ~(size_t)127) + (size_t)lc.wq_warps * wq_warp_bytes(k, ncap, packet);
     long long ctas = lc.sm_count;
     const long long useful = (items + 32 * k * lc.wq_warps - 1) / (32 * k * lc.wq_warps);
     if (ctas > useful) ctas = useful;
-#define RAYB200_WQ(KK, SP, A, S) render_warpqueue_kernel<KK, SP, A, S><<<(unsigned)ctas, wthreads, wsmem, stream>>>(p, ncap, lc.wq_packet, lc.wq_refill)
-#define RAYB200_WQ2(KK, SP)                                                               \
+#define RAYB200_WQ(KK, SP, PK, A, S) \
+  render_warpqueue_kernel<KK, SP, PK, A, S><<<(unsigned)ctas, wthreads, wsmem, stream>>>(p, ncap, lc.wq_packet, lc.wq_refill)
+#define RAYB200_WQ2(KK, SP, PK)                                                           \
   do {                                                                                    \
-    if (all_nodes && sph) RAYB200_WQ(KK, SP, true, true);                                 \
-    else if (all_nodes) RAYB200_WQ(KK, SP, true, false);                                  \
-    else if (sph) RAYB200_WQ(KK, SP, false, true);                                        \
-    else RAYB200_WQ(KK, SP, false, false);                                                \
+    if (all_nodes && sph) RAYB200_WQ(KK, SP, PK, true, true);                             \
+    else if (all_nodes) RAYB200_WQ(KK, SP, PK, true, false);                              \
+    else if (sph) RAYB200_WQ(KK, SP, PK, false, true);                                    \
+    else RAYB200_WQ(KK, SP, PK, false, false);                                            \
+  } while (0)
+#define RAYB200_WQ3(KK, SP)                                                               \
+  do {                                                                                    \
+    if (packet) RAYB200_WQ2(KK, SP, true); else RAYB200_WQ2(KK, SP, false);               \
   } while (0)
     const bool spread = p.sample_buf != nullptr;
-    if (k == 1) { if (spread) RAYB200_WQ2(1, true); else RAYB200_WQ2(1, false); }
-    else { if (spread) RAYB200_WQ2(2, true); else RAYB200_WQ2(2, false); }
+    if (k == 1) { if (spread) RAYB200_WQ3(1, true); else RAYB200_WQ3(1, false); }
+    else { if (spread) RAYB200_WQ3(2, true); else RAYB200_WQ3(2, false); }
+#undef RAYB200_WQ3
 #undef RAYB200_WQ2
 #undef RAYB200_WQ
     (*launches)++;

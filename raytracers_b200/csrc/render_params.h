@@ -88,9 +88,9 @@ __host__ __device__ inline int wq_node_capacity(int k, int max_depth) {
   const int c = 32 * k + 64 * (max_depth + 1);
   return c < 256 ? 256 : (c > 1024 ? 1024 : c);
 }
-__host__ __device__ inline size_t wq_warp_bytes(int k, int ncap) {
+__host__ __device__ inline size_t wq_warp_bytes(int k, int ncap, bool packet) {
   const size_t r = 32 * (size_t)k;
-  return ((r * (16 * 5 + 8 + 4) + 2 * kWqRing * 4 + 2 * kWqPacketStack * 4 + kWqLeafStack * 4 + (size_t)ncap * 4) + 127) & ~(size_t)127;
+  return ((r * (16 * 5 + 8 + 4) + 2 * kWqRing * 4 + (packet ? 2 * kWqPacketStack * 4 : 0) + kWqLeafStack * 4 + (size_t)ncap * 4) + 127) & ~(size_t)127;
 }
 cudaError_t configure_kernels(int max_dynamic_smem);
 
