@@ -9,6 +9,13 @@
  *   - the explicit C entry points below (plain pointers and sizes; device pointers are raw
  *     CUDA device addresses, e.g. torch.Tensor.data_ptr()).
  *
+ * Multi-GPU.  Two ways: (a) one process per GPU (torchrun): ray_b200_context_set_shard + ray_b200_render_shard_into, an
+ * NCCL gather by the host, ray_b200_detile — see raytracers_b200/distributed.py; (b) ONE process, several devices:
+ * RAY_GPUS=N (or tuning parameter "gpus") makes the context drive devices d..d+N-1; futhark_entry_prepare_scene replicates
+ * the scene, futhark_entry_render renders interleaved tiles on every device and pulls the shards to device d with peer
+ * copies over NVLink.  This is the mode an unmodified futhark/main.c uses.  In mode (b) the raw-pointer entry points
+ * (ray_b200_render_into, ray_b200_render_shard_into) keep addressing device d's shard only.
+ *
  * spp semantics: sample s of pixel (row j, column i) uses
  *   u = (f32(i) + ox_s) / f32(W),  v = (f32(H - j) + oy_s) / f32(H),
  *   ox_s = frac(f32(s) * 0.7548776662f), oy_s = frac(f32(s) * 0.5698402909f)   [ox_0 = oy_0 = 0]

@@ -72,6 +72,8 @@ def load_library():
         "futhark_context_config_set_logging": (None, [vp, C.c_int]),
         "futhark_context_config_set_device": (None, [vp, C.c_char_p]),
         "futhark_context_config_set_tuning_param": (C.c_int, [vp, C.c_char_p, C.c_size_t]),
+        "futhark_get_tuning_param_count": (C.c_int, []),
+        "futhark_get_tuning_param_name": (C.c_char_p, [C.c_int]),
         "futhark_context_new": (vp, [vp]),
         "futhark_context_free": (None, [vp]),
         "futhark_context_sync": (C.c_int, [vp]),

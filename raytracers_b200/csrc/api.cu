@@ -26,6 +26,7 @@ struct futhark_context_config {
   int32_t spp = 1;
   int32_t kernel = RAY_B200_KERNEL_AUTO;
   int32_t rank = 0, world = 1;
+  int32_t gpus = 1;  // > 1: this ONE process drives that many devices (RAY_GPUS; the drop-in multi-GPU mode of main.c)
   int32_t blocks_per_sm = 4, smem_budget = 48 * 1024, refill_min = 8, tail_from = 8;
   int32_t wq_warps = 24, wq_k = 1, wq_spread = 1, wq_packet = -1, wq_refill = 1, permute = 1, host_build = 0;
   std::string cache_file;
@@ -49,7 +50,15 @@ struct futhark_context {
   struct PinnedBlock { unsigned char *ptr; size_t bytes; cudaEvent_t last_use; };
   std::vector<PinnedBlock> pinned_cache;    // page-locked upload buffers of freed prepared scenes, reused by the next prepare_scene
   BvhBuildResult *d_build_result = nullptr, *h_build_result = nullptr;  // device scratch / page-locked host mirror
-  int32_t plan_wq_warps = 0, plan_wq_packet = 0;                // warps per CTA the warp-queue kernel will use for the frame being set up
+  int32_t plan_wq_warps = 0, plan_wq_packet = 0;
+  // single-process multi-GPU (cfg.gpus > 1): one helper context per extra device; this context is rank 0 and owns them
+  std::vector<futhark_context *> peers;
+  bool is_peer = false;
+  int32_t *peer_tiles = nullptr;        // helper context: this device's compact tile buffer (grow-only)
+  size_t peer_tiles_bytes = 0;
+  cudaEvent_t peer_done = nullptr;      // helper context: its shard has been rendered
+  int32_t *gathered = nullptr;          // rank 0: [gpus][tiles_padded][32] staging for the de-tiling kernel (grow-only)
+  size_t gathered_bytes = 0;                // warps per CTA the warp-queue kernel will use for the frame being set up
   float4 *sample_buf = nullptr;             // warp-queue kernel, spp > 1: per-warp finished-sample colours
   size_t sample_buf_bytes = 0;
   bool profiling_paused = false;
@@ -68,6 +77,7 @@ struct futhark_opaque_prepared_scene {
   float root_box[6];
   int32_t max_depth = 0, stale_nodes = 0, refit_sweeps = 0;
   int64_t n = 0;
+  std::vector<futhark_opaque_prepared_scene *> peer_prepared;  // single-process multi-GPU: the same scene on every helper device
   DeviceBvh dev;    // everything resident in HBM (one stream-ordered allocation): packed BVH2C + the Karras-order LBVH
   unsigned char *pinned = nullptr;     // page-locked upload buffer (sphere records, or the host-built arrays)
   size_t pinned_bytes = 0;
@@ -120,7 +130,7 @@ int parse_kernel(const char *v, int dflt) {
   return atoi(v);
 }
 
-const char *kTuningNames[] = {"kernel", "spp", "blocks_per_sm", "smem_budget", "refill_min", "tail_from", "wq_warps", "wq_k", "wq_spread", "wq_packet", "wq_refill", "permute", "host_build", "rank", "world"};
+const char *kTuningNames[] = {"kernel", "spp", "blocks_per_sm", "smem_budget", "refill_min", "tail_from", "wq_warps", "wq_k", "wq_spread", "wq_packet", "wq_refill", "permute", "host_build", "rank", "world", "gpus"};
 constexpr int kNumTuning = sizeof(kTuningNames) / sizeof(kTuningNames[0]);
 
 bool bad_ctx(futhark_context *ctx) { return ctx == nullptr || !ctx->ok; }
@@ -446,6 +456,7 @@ int futhark_context_config_set_tuning_param(struct futhark_context_config *cfg, 
   else if (!strcmp(name, "host_build")) cfg->host_build = (int32_t)v;
   else if (!strcmp(name, "rank")) cfg->rank = (int32_t)v;
   else if (!strcmp(name, "world")) cfg->world = (int32_t)v;
+  else if (!strcmp(name, "gpus")) cfg->gpus = (int32_t)v;
   else return 1;
   return 0;
 }
@@ -455,11 +466,13 @@ struct futhark_context *futhark_context_new(struct futhark_context_config *cfg) 
   if (!ctx) return nullptr;
   if (cfg) ctx->cfg = *cfg;
   // environment overrides: the only extension channel an unmodified futhark/main.c has
-  ctx->cfg.device = env_int("RAY_DEVICE", ctx->cfg.device);
+  const bool helper = cfg && cfg->gpus < 0;  // helper context of a single-process multi-GPU context: config is final
+  if (!helper) ctx->cfg.device = env_int("RAY_DEVICE", ctx->cfg.device);
   ctx->cfg.spp = env_int("RAY_SPP", ctx->cfg.spp);
   ctx->cfg.kernel = parse_kernel(getenv("RAY_KERNEL"), ctx->cfg.kernel);
-  ctx->cfg.rank = env_int("RAY_RANK", ctx->cfg.rank);
-  ctx->cfg.world = env_int("RAY_WORLD", ctx->cfg.world);
+  if (!helper) ctx->cfg.rank = env_int("RAY_RANK", ctx->cfg.rank);
+  if (!helper) ctx->cfg.world = env_int("RAY_WORLD", ctx->cfg.world);
+  if (!(cfg && cfg->gpus < 0)) ctx->cfg.gpus = env_int("RAY_GPUS", ctx->cfg.gpus);
   ctx->cfg.blocks_per_sm = env_int("RAY_BLOCKS_PER_SM", ctx->cfg.blocks_per_sm);
   ctx->cfg.smem_budget = env_int("RAY_SMEM_BUDGET", ctx->cfg.smem_budget);
   ctx->cfg.refill_min = env_int("RAY_REFILL_MIN", ctx->cfg.refill_min);
@@ -507,11 +520,50 @@ struct futhark_context *futhark_context_new(struct futhark_context_config *cfg) 
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
   }
   ctx->ok = true;
+  // single-process multi-GPU: helper contexts on devices device+1 .. device+gpus-1 (peer access enabled both ways)
+  if (ctx->cfg.gpus > 1 && !(cfg && cfg->gpus < 0)) {
+    if (ctx->cfg.device + ctx->cfg.gpus > ndev) {
+      ctx->ok = false;
+      set_error(ctx, "futhark_context_new: RAY_GPUS=%d needs devices %d..%d but only %d are visible", ctx->cfg.gpus, ctx->cfg.device,
+                ctx->cfg.device + ctx->cfg.gpus - 1, ndev);
+      return ctx;
+    }
+    for (int r = 1; r < ctx->cfg.gpus; r++) {
+      futhark_context_config pc = ctx->cfg;
+      pc.device = ctx->cfg.device + r;
+      pc.rank = r; pc.world = ctx->cfg.gpus;
+      pc.gpus = -1;  // marks a helper: no recursion, no environment override of the device
+      futhark_context *peer = futhark_context_new(&pc);
+      if (!peer || !peer->ok) {
+        char *pe = peer ? futhark_context_get_error(peer) : nullptr;
+        ctx->ok = false;
+        set_error(ctx, "futhark_context_new: helper context on device %d failed: %s", pc.device, pe ? pe : "?");
+        free(pe);
+        if (peer) futhark_context_free(peer);
+        return ctx;
+      }
+      peer->is_peer = true;
+      cudaSetDevice(pc.device);
+      cudaEventCreateWithFlags(&peer->peer_done, cudaEventDisableTiming);
+      cudaDeviceEnablePeerAccess(ctx->cfg.device, 0);
+      cudaSetDevice(ctx->cfg.device);
+      cudaDeviceEnablePeerAccess(pc.device, 0);
+      cudaGetLastError();  // "already enabled" is fine
+      ctx->peers.push_back(peer);
+    }
+    ctx->cfg.rank = 0; ctx->cfg.world = ctx->cfg.gpus;
+    cudaSetDevice(ctx->cfg.device);
+  }
   return ctx;
 }
 
 void futhark_context_free(struct futhark_context *ctx) {
   if (!ctx) return;
+  for (futhark_context *peer : ctx->peers) futhark_context_free(peer);
+  ctx->peers.clear();
+  if (ctx->peer_tiles) { cudaSetDevice(ctx->cfg.device); cudaFree(ctx->peer_tiles); }
+  if (ctx->peer_done) cudaEventDestroy(ctx->peer_done);
+  if (ctx->gathered) { cudaSetDevice(ctx->cfg.device); cudaFree(ctx->gathered); }
   if (ctx->ok) {
     cudaSetDevice(ctx->cfg.device);
     cudaStreamSynchronize(ctx->stream);
@@ -534,6 +586,10 @@ void futhark_context_free(struct futhark_context *ctx) {
 int futhark_context_sync(struct futhark_context *ctx) {
   if (bad_ctx(ctx)) return 1;
   std::lock_guard<std::mutex> g(ctx->mu);
+  for (futhark_context *peer : ctx->peers) {
+    if (futhark_context_sync(peer)) { char *pe = futhark_context_get_error(peer); set_error(ctx, "helper device: %s", pe ? pe : "?"); free(pe); return 1; }
+  }
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return 0;
 }
@@ -658,6 +714,9 @@ int futhark_free_opaque_prepared_scene(struct futhark_context *ctx, struct futha
   if (!obj) return 0;
   if (ctx && ctx->ok) {
     std::lock_guard<std::mutex> g(ctx->mu);
+    for (size_t k = 0; k < obj->peer_prepared.size() && k < ctx->peers.size(); k++)
+      futhark_free_opaque_prepared_scene(ctx->peers[k], obj->peer_prepared[k]);
+    cudaSetDevice(ctx->cfg.device);
     free_prepared_device(ctx, obj);  // stream-ordered: a render still using it finishes first
   }
   delete obj;
@@ -718,6 +777,19 @@ int futhark_entry_prepare_scene(struct futhark_context *ctx, struct futhark_opaq
   p->h = h; p->w = w;
   p->cam = make_camera(p->host, h, w);
   if (prepare_any(ctx, p)) { free_prepared_device(ctx, p); delete p; return 1; }
+  for (futhark_context *peer : ctx->peers) {  // the scene is replicated: every device builds its own LBVH
+    futhark_opaque_prepared_scene *pp = nullptr;
+    if (futhark_entry_prepare_scene(peer, &pp, h, w, scene)) {
+      char *pe = futhark_context_get_error(peer);
+      set_error(ctx, "prepare_scene on helper device %d: %s", peer->cfg.device, pe ? pe : "?");
+      free(pe);
+      for (size_t k = 0; k < p->peer_prepared.size(); k++) futhark_free_opaque_prepared_scene(ctx->peers[k], p->peer_prepared[k]);
+      free_prepared_device(ctx, p); delete p;
+      return 1;
+    }
+    p->peer_prepared.push_back(pp);
+  }
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
   *out0 = p;
   return 0;
 }
@@ -734,6 +806,58 @@ int ray_b200_entry_render_spp(struct futhark_context *ctx, struct futhark_i32_2d
   cudaError_t e = cudaMallocAsync(&img->dev, bytes ? bytes : 4, ctx->stream);
   if (e != cudaSuccess) { set_error(ctx, "render: cudaMallocAsync: %s", cudaGetErrorString(e)); delete img; return 1; }
   RenderParams P;
+  if (!ctx->peers.empty()) {
+    // single-process multi-GPU: every device renders its tiles into a compact buffer, device 0 pulls them over
+    // NVLink (peer copies ordered by events) and de-tiles — the same data flow as the one-process-per-GPU path,
+    // with cudaMemcpyPeerAsync in place of the NCCL gather
+    const int world = (int)ctx->peers.size() + 1;
+    const int64_t padded = ray_b200_shard_tiles_padded(h, w, world);
+    const size_t shard_bytes = (size_t)padded * kTilePixels * sizeof(int32_t);
+    auto fail = [&](const char *what) { set_error(ctx, "render (multi-GPU): %s", what); cudaFreeAsync(img->dev, ctx->stream); delete img; return 1; };
+    if (p->peer_prepared.size() != ctx->peers.size()) return fail("prepared scene was not prepared by this context");
+    if (ctx->gathered_bytes < shard_bytes * world) {
+      cudaStreamSynchronize(ctx->stream);
+      if (ctx->gathered) cudaFree(ctx->gathered);
+      ctx->gathered = nullptr; ctx->gathered_bytes = 0;
+      if (cudaMalloc(&ctx->gathered, shard_bytes * world) != cudaSuccess) return fail("out of device memory");
+      ctx->gathered_bytes = shard_bytes * world;
+    }
+    for (int r = 1; r < world; r++) {
+      futhark_context *peer = ctx->peers[(size_t)r - 1];
+      cudaSetDevice(peer->cfg.device);
+      if (peer->peer_tiles_bytes < shard_bytes) {
+        cudaStreamSynchronize(peer->stream);
+        if (peer->peer_tiles) cudaFree(peer->peer_tiles);
+        peer->peer_tiles = nullptr; peer->peer_tiles_bytes = 0;
+        if (cudaMalloc(&peer->peer_tiles, shard_bytes) != cudaSuccess) { cudaSetDevice(ctx->cfg.device); return fail("out of device memory on a helper device"); }
+        peer->peer_tiles_bytes = shard_bytes;
+      }
+      if (ray_b200_render_shard_into(peer, peer->peer_tiles, h, w, spp, p->peer_prepared[(size_t)r - 1])) {
+        char *pe = futhark_context_get_error(peer);
+        cudaSetDevice(ctx->cfg.device);
+        set_error(ctx, "render on helper device %d: %s", peer->cfg.device, pe ? pe : "?");
+        free(pe);
+        cudaFreeAsync(img->dev, ctx->stream); delete img;
+        return 1;
+      }
+      cudaEventRecord(peer->peer_done, peer->stream);
+    }
+    cudaSetDevice(ctx->cfg.device);
+    // rank 0's own shard straight into slot 0 of the gather buffer
+    if (fill_params(ctx, p, h, w, spp, 0, world, ctx->gathered, nullptr, true, P)) { cudaFreeAsync(img->dev, ctx->stream); delete img; return 1; }
+    if (P.local_tiles < padded)
+      cudaMemsetAsync(ctx->gathered + P.local_tiles * kTilePixels, 0, (size_t)(padded - P.local_tiles) * kTilePixels * 4, ctx->stream);
+    if (do_render(ctx, P)) { cudaFreeAsync(img->dev, ctx->stream); delete img; return 1; }
+    for (int r = 1; r < world; r++) {
+      futhark_context *peer = ctx->peers[(size_t)r - 1];
+      cudaStreamWaitEvent(ctx->stream, peer->peer_done, 0);
+      cudaMemcpyPeerAsync(ctx->gathered + (size_t)r * padded * kTilePixels, ctx->cfg.device, peer->peer_tiles, peer->cfg.device, shard_bytes, ctx->stream);
+    }
+    launch_detile(ctx->gathered, img->dev, h, w, world, padded, ctx->stream, &ctx->launches);
+    if (cudaGetLastError() != cudaSuccess) return fail("de-tiling launch failed");
+    *out0 = img;
+    return 0;
+  }
   // With a shard configured, the row-major frame only receives this rank's tiles; clear the rest.
   if (ctx->cfg.world > 1) cudaMemsetAsync(img->dev, 0, bytes, ctx->stream);
   if (fill_params(ctx, p, h, w, spp, ctx->cfg.rank, ctx->cfg.world, img->dev, nullptr, false, P) || do_render(ctx, P)) {

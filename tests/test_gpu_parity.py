@@ -258,6 +258,44 @@ def test_error_behaviour(R):
         assert img.shape == (8, 8)
 
 
+def test_array_and_misc_api(R):
+    """The rest of the generated-API surface: array constructors/accessors, report, cache clearing, config flags."""
+    import ctypes as C
+    L = R.load_library()
+    cfg = L.futhark_context_config_new()
+    L.futhark_context_config_set_debugging(cfg, 0)
+    L.futhark_context_config_set_profiling(cfg, 1)
+    L.futhark_context_config_set_logging(cfg, 0)
+    L.futhark_context_config_set_device(cfg, b"#0")
+    assert L.futhark_context_config_set_tuning_param(cfg, b"no_such_param", 1) == 1
+    assert L.futhark_context_config_set_tuning_param(cfg, b"spp", 1) == 0
+    names = [L.futhark_get_tuning_param_name(i) for i in range(L.futhark_get_tuning_param_count())] if hasattr(L, "futhark_get_tuning_param_count") else []
+    ctxh = L.futhark_context_new(cfg)
+    L.futhark_context_config_free(cfg)
+    assert ctxh and not L.futhark_context_get_error(ctxh)
+    data = np.arange(6 * 9, dtype=np.int32).reshape(6, 9)
+    arr = L.futhark_new_i32_2d(ctxh, data.ctypes.data, 6, 9)
+    assert arr
+    shp = L.futhark_shape_i32_2d(ctxh, arr)
+    assert (shp[0], shp[1]) == (6, 9)
+    back = np.zeros_like(data)
+    assert L.futhark_values_i32_2d(ctxh, arr, back.ctypes.data) == 0
+    np.testing.assert_array_equal(back, data)
+    raw = L.futhark_values_raw_i32_2d(ctxh, arr)
+    assert raw
+    alias = L.futhark_new_raw_i32_2d(ctxh, raw, 6, 9)     # wraps, does not own
+    back2 = np.zeros_like(data)
+    assert L.futhark_values_i32_2d(ctxh, alias, back2.ctypes.data) == 0
+    np.testing.assert_array_equal(back2, data)
+    assert L.futhark_free_i32_2d(ctxh, alias) == 0 and L.futhark_free_i32_2d(ctxh, arr) == 0
+    assert L.futhark_context_clear_caches(ctxh) == 0 and L.futhark_context_sync(ctxh) == 0
+    rep = L.futhark_context_report(ctxh)
+    assert b"ray_b200" in C.string_at(rep)
+    C.CDLL(None).free.argtypes = [C.c_void_p]
+    C.CDLL(None).free(rep)
+    L.futhark_context_free(ctxh)
+
+
 def test_store_restore_and_reupload(R, oracle):
     h, w = 40, 56
     want, _, _ = oracle.render_scene("irreg", h, w)
@@ -308,6 +346,41 @@ def test_sharded_render_equals_single_gpu(R, oracle, world):
         ctx.detile(gathered.data_ptr(), frame.data_ptr(), h, w, world)
         torch.cuda.synchronize()
     assert_same(frame.cpu().numpy(), want, f"sharded world={world}")
+
+
+def _device_count():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.skipif(_device_count() < 2, reason="needs at least 2 GPUs in this process")
+def test_single_process_multi_gpu_context(R, oracle, tmp_path):
+    """RAY_GPUS / tuning "gpus": ONE process (e.g. the unmodified main.c) drives several devices — scene replicated,
+    tiles interleaved, shards pulled to device 0 with peer copies, de-tiled.  Frame must equal the oracle's."""
+    g = min(_device_count(), 4)
+    for name, h, w, spp in (("irreg", 90, 122, 1), ("rgbbox", 64, 96, 3)):
+        want, _, _ = oracle.Scene.named(name).prepare(h, w).render(h, w, spp=spp)
+        with R.Context(gpus=g) as ctx:
+            pr = ctx.prepare_scene(h, w, ctx.scene(name))
+            img = ctx.render(h, w, pr, spp=spp)
+            ctx.sync()
+            assert_same(img.values(), want, f"{name} gpus={g}")
+            img2 = ctx.render(h, w, pr, spp=spp)      # buffers are reused across frames
+            assert_same(img2.values(), want, f"{name} gpus={g} second frame")
+            img.free(); img2.free(); pr.free()
+    exe = os.path.join(ROOT, "examples", "_built", "main_ref")
+    if os.path.exists(exe):
+        ppm = str(tmp_path / "mg.ppm")
+        r = subprocess.run([exe, "-s", "irreg", "-n", "120", "-m", "160", "-r", "2", "-f", ppm], capture_output=True, text=True,
+                           env=dict(os.environ, RAY_GPUS=str(g)))
+        assert r.returncode == 0, r.stderr + r.stdout
+        tok = open(ppm).read().split()
+        rgb = np.array(tok[4:], dtype=np.int32).reshape(120, 160, 3)
+        want, _, _ = oracle.render_scene("irreg", 120, 160)
+        assert_same((rgb[..., 0] << 16) | (rgb[..., 1] << 8) | rgb[..., 2], want, f"main.c RAY_GPUS={g}")
 
 
 def test_reference_driver_binary_runs_against_the_library(tmp_path, oracle):
