@@ -43,7 +43,7 @@ def dram_traffic_per_launch():
     try:
         with open(os.path.join(ROOT, "profiles", "dram_traffic.json")) as f:
             d = json.load(f)
-        return {k: int(d[k]) for k in SCENES}
+        return {k: int(d[k]) for k in SCENES} if H == 1000 and SPP == 64 else None
     except Exception:
         return None
 
@@ -164,7 +164,7 @@ def run_reference(args):
         secs += t
     wall = time.perf_counter() - t_all
     value = segs / secs / 1e6
-    sample = f"rows j%{ROW_STEP}==0 of both 1000x1000 frames at {SPP} spp (1/{ROW_STEP} of a step) per step"
+    sample = f"rows j%{ROW_STEP}==0 of every {W}x{H} frame of the step at {SPP} spp (1/{ROW_STEP} of a step) per step"
     line = {
         "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": "Mrays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * wall / args.steps, 3),
@@ -348,7 +348,7 @@ def run_ours(args):
     one_spp = None
     if rank == 0 and world == 1:
         one_spp = {}
-        for name in SCENES:
+        for name in (SCENES if H <= 2000 else ()):
             ms = []
             for _ in range(7):
                 ctx.render_into(frames[name].data_ptr(), H, W, prepared[name], spp=1)
@@ -388,7 +388,7 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         segs, secs, cores = cpu_sample()
         cpu = {"value": round(segs / secs / 1e6, 3), "unit": "Mrays/s", "cores": cores, "cgroup_cpu_quota": host_cpu_quota(), "kind": "port",
-               "sample": f"rows j%{ROW_STEP}==0 of both 1000x1000 frames at {SPP} spp (1/{ROW_STEP} of a step), {secs:.1f} s"}
+               "sample": f"rows j%{ROW_STEP}==0 of every {W}x{H} frame of the step at {SPP} spp (1/{ROW_STEP} of a step), {secs:.1f} s"}
 
     if rank == 0:
         line = {
@@ -411,6 +411,20 @@ def run_ours(args):
     return 0
 
 
+WORKLOADS = {
+    # name: (scenes, H, W, spp, metric, workload description, rows the CPU legs sample)
+    "headline": (("rgbbox", "irreg"), 1000, 1000, 64, "Mrays/s (ray segments/s) rgbbox+irreg 1000x1000",
+                 "rgbbox 1000x1000 64spp + irreg 1000x1000 64spp per step (BASELINE.json configs[1]+configs[2])", 8),
+    "irreg4000": (("irreg",), 4000, 4000, 256, "Mrays/s (ray segments/s) irreg 4000x4000 256spp",
+                  "irreg 4000x4000 256spp per step (BASELINE.json configs[3])", 512),
+}
+
+
+def select_workload(name):
+    global SCENES, H, W, SPP, METRIC, WORKLOAD, ROW_STEP
+    SCENES, H, W, SPP, METRIC, WORKLOAD, ROW_STEP = WORKLOADS[name]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -421,7 +435,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--extra", action="store_true",
                     help="also measure (once, outside the timed steps) BASELINE configs[3] and [4]: irreg 4000x4000 256spp and the 1M-sphere scene")
+    ap.add_argument("--workload", default="headline", choices=sorted(WORKLOADS),
+                    help="headline = BASELINE configs[1]+[2] (the default the driver measures); irreg4000 = configs[3]")
     args = ap.parse_args()
+    select_workload(args.workload)
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)
