@@ -310,6 +310,7 @@ int do_render(futhark_context *ctx, RenderParams &P) {
 // Device memory goes back to the stream-ordered pool (ordered after any render still using it);
 // the page-locked upload buffer goes to the context's cache together with the event that guards it.
 void free_prepared_device(futhark_context *ctx, futhark_opaque_prepared_scene *p) {
+  cudaSetDevice(ctx->cfg.device);
   if (p->dev.block) cudaFreeAsync(p->dev.block, ctx->stream);
   if (p->pinned) {
     if (ctx->pinned_cache.size() < 4) ctx->pinned_cache.push_back({p->pinned, p->pinned_bytes, p->pinned_event});
@@ -586,6 +587,7 @@ void futhark_context_free(struct futhark_context *ctx) {
 int futhark_context_sync(struct futhark_context *ctx) {
   if (bad_ctx(ctx)) return 1;
   std::lock_guard<std::mutex> g(ctx->mu);
+  cudaSetDevice(ctx->cfg.device);  // helper contexts of the single-process multi-GPU mode switch devices
   for (futhark_context *peer : ctx->peers) {
     if (futhark_context_sync(peer)) { char *pe = futhark_context_get_error(peer); set_error(ctx, "helper device: %s", pe ? pe : "?"); free(pe); return 1; }
   }
@@ -621,6 +623,7 @@ void futhark_context_unpause_profiling(struct futhark_context *ctx) { if (ctx) c
 int futhark_context_clear_caches(struct futhark_context *ctx) {
   if (bad_ctx(ctx)) return 1;
   std::lock_guard<std::mutex> g(ctx->mu);
+  cudaSetDevice(ctx->cfg.device);  // helper contexts of the single-process multi-GPU mode switch devices
   cudaMemPool_t pool;
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   if (cudaDeviceGetDefaultMemPool(&pool, ctx->cfg.device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
@@ -631,6 +634,7 @@ int futhark_context_clear_caches(struct futhark_context *ctx) {
 struct futhark_i32_2d *futhark_new_i32_2d(struct futhark_context *ctx, const int32_t *data, int64_t d0, int64_t d1) {
   if (bad_ctx(ctx) || d0 < 0 || d1 < 0) return nullptr;
   std::lock_guard<std::mutex> g(ctx->mu);
+  cudaSetDevice(ctx->cfg.device);  // helper contexts of the single-process multi-GPU mode switch devices
   futhark_i32_2d *a = new futhark_i32_2d;
   a->shape[0] = d0; a->shape[1] = d1;
   const size_t bytes = (size_t)d0 * d1 * sizeof(int32_t);
@@ -649,6 +653,7 @@ int futhark_free_i32_2d(struct futhark_context *ctx, struct futhark_i32_2d *arr)
   if (bad_ctx(ctx)) return 1;
   if (!arr) return 0;
   std::lock_guard<std::mutex> g(ctx->mu);
+  cudaSetDevice(ctx->cfg.device);  // helper contexts of the single-process multi-GPU mode switch devices
   if (arr->owned && arr->dev) CUDA_TRY(ctx, cudaFreeAsync(arr->dev, ctx->stream));
   delete arr;
   return 0;
@@ -656,6 +661,7 @@ int futhark_free_i32_2d(struct futhark_context *ctx, struct futhark_i32_2d *arr)
 int futhark_values_i32_2d(struct futhark_context *ctx, struct futhark_i32_2d *arr, int32_t *data) {
   if (bad_ctx(ctx)) return 1;
   std::lock_guard<std::mutex> g(ctx->mu);
+  cudaSetDevice(ctx->cfg.device);  // helper contexts of the single-process multi-GPU mode switch devices
   if (!arr || !data) { set_error(ctx, "futhark_values_i32_2d: null argument"); return 1; }
   const size_t bytes = (size_t)arr->shape[0] * arr->shape[1] * sizeof(int32_t);
   CUDA_TRY(ctx, cudaMemcpyAsync(data, arr->dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
@@ -879,6 +885,7 @@ int futhark_entry_render(struct futhark_context *ctx, struct futhark_i32_2d **ou
 int ray_b200_context_set_stream(struct futhark_context *ctx, void *s) {
   if (bad_ctx(ctx)) return 1;
   std::lock_guard<std::mutex> g(ctx->mu);
+  cudaSetDevice(ctx->cfg.device);  // helper contexts of the single-process multi-GPU mode switch devices
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
   return 0;
@@ -905,6 +912,7 @@ int ray_b200_context_device(struct futhark_context *ctx) { return ctx ? ctx->cfg
 int ray_b200_context_last_render_ms(struct futhark_context *ctx, float *ms) {
   if (bad_ctx(ctx) || !ms) return 1;
   std::lock_guard<std::mutex> g(ctx->mu);
+  cudaSetDevice(ctx->cfg.device);  // helper contexts of the single-process multi-GPU mode switch devices
   if (!ctx->have_timing) { set_error(ctx, "no render has been issued yet"); return 1; }
   CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev_stop));
   CUDA_TRY(ctx, cudaEventElapsedTime(ms, ctx->ev_start, ctx->ev_stop));
@@ -957,6 +965,7 @@ int ray_b200_prepared_dump(struct futhark_context *ctx, const struct futhark_opa
                            int32_t *left, int32_t *right, int32_t *parent, float *boxes) {
   if (bad_ctx(ctx)) return 1;
   std::lock_guard<std::mutex> g(ctx->mu);
+  cudaSetDevice(ctx->cfg.device);  // helper contexts of the single-process multi-GPU mode switch devices
   if (!p || !p->dev.block) { set_error(ctx, "prepared_dump: invalid prepared scene"); return 1; }
   const size_t n = (size_t)p->n, ni = n - 1;
   const cudaMemcpyKind k = cudaMemcpyDeviceToHost;
@@ -974,6 +983,7 @@ int ray_b200_prepared_packed(struct futhark_context *ctx, const struct futhark_o
                              float *geom, float *colour) {
   if (bad_ctx(ctx)) return 1;
   std::lock_guard<std::mutex> g(ctx->mu);
+  cudaSetDevice(ctx->cfg.device);  // helper contexts of the single-process multi-GPU mode switch devices
   if (!p || !p->dev.block) { set_error(ctx, "prepared_packed: invalid prepared scene"); return 1; }
   const size_t n = (size_t)p->n, ni = n - 1;
   const cudaMemcpyKind k = cudaMemcpyDeviceToHost;
