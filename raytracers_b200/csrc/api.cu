@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -351,7 +352,15 @@ int acquire_pinned(futhark_context *ctx, futhark_opaque_prepared_scene *p, size_
 
 // prepare_scene, device path (default): H2D of the sphere records from page-locked memory, then the whole
 // LBVH build + packing as kernels on the context's stream (bvh_build.cu).
+double now_us() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
+}
+
 int prepare_on_device(futhark_context *ctx, futhark_opaque_prepared_scene *p) {
+  const bool timing = ctx->cfg.debugging != 0;
+  const double t0 = timing ? now_us() : 0.0;
   const size_t n = p->host.spheres.size();
   const size_t sph_bytes = n * sizeof(SphereRec);
   if (acquire_pinned(ctx, p, sph_bytes)) return 1;
@@ -360,13 +369,18 @@ int prepare_on_device(futhark_context *ctx, futhark_opaque_prepared_scene *p) {
   CUDA_TRY(ctx, cudaMallocAsync(&d_spheres, sph_bytes, ctx->stream));
   CUDA_TRY(ctx, cudaMemcpyAsync(d_spheres, p->pinned, sph_bytes, cudaMemcpyHostToDevice, ctx->stream));
   CUDA_TRY(ctx, cudaEventRecord(p->pinned_event, ctx->stream));
+  const double t1 = timing ? now_us() : 0.0;
   p->refit_sweeps = (int32_t)log2f((float)(int64_t)n) + 2;  // bvh.fut:47, host libm as in the reference's C backend
   if (p->dev.block) { CUDA_TRY(ctx, cudaFreeAsync(p->dev.block, ctx->stream)); p->dev = DeviceBvh(); }
   CUDA_TRY(ctx, build_bvh_device(d_spheres, (int64_t)n, p->refit_sweeps, p->dev, ctx->d_build_result, ctx->stream, &ctx->launches));
   CUDA_TRY(ctx, cudaFreeAsync(d_spheres, ctx->stream));
   // the host needs the tree depth (stack sizing) and the root box (kernel parameter) before the first render
+  const double t2 = timing ? now_us() : 0.0;
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_build_result, ctx->d_build_result, sizeof(BvhBuildResult), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (timing)
+    fprintf(ctx->log ? ctx->log : stderr, "[ray_b200] prepare_scene n=%zu: stage+H2D enqueue %.0f us, build enqueue %.0f us, wait %.0f us\n", n,
+            t1 - t0, t2 - t1, now_us() - t2);
   memcpy(p->root_box, ctx->h_build_result->root_box, sizeof p->root_box);
   p->max_depth = ctx->h_build_result->max_depth;
   p->stale_nodes = ctx->h_build_result->stale_nodes;
@@ -485,6 +499,7 @@ struct futhark_context *futhark_context_new(struct futhark_context_config *cfg) 
   ctx->cfg.wq_refill = env_int("RAY_WQ_REFILL", ctx->cfg.wq_refill);
   ctx->cfg.permute = env_int("RAY_PERMUTE", ctx->cfg.permute);
   ctx->cfg.host_build = env_int("RAY_HOST_BUILD", ctx->cfg.host_build);
+  ctx->cfg.debugging = env_int("RAY_DEBUG", ctx->cfg.debugging);
   memset(&ctx->wf, 0, sizeof ctx->wf);
 
   auto fail = [&](const char *what, cudaError_t e) {

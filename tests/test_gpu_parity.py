@@ -402,6 +402,26 @@ def test_reference_driver_binary_runs_against_the_library(tmp_path, oracle):
         assert_same((rgb[..., 0] << 16) | (rgb[..., 1] << 8) | rgb[..., 2], want, f"main.c {name}")
 
 
+def test_million_sphere_scene_kernels_and_builders_agree(R):
+    """BASELINE configs[4]'s scene (1 M random spheres, tree depth ~25) is far too slow for the CPU oracle, so the two
+    independent LBVH builders (device kernels vs host C++) and two independent traversals (lane-bound stack walk vs
+    item queues with packet walk) are checked against each other: identical trees, identical frames."""
+    n, h, w, spp = 1000000, 256, 320, 2
+    with R.Context(kernel="warpqueue") as ctx, R.Context(kernel="mega", host_build=1) as ctx_h:
+        pr = ctx.prepare_scene(h, w, ctx.scene_random(n, 1))
+        pr_h = ctx_h.prepare_scene(h, w, ctx_h.scene_random(n, 1))
+        a, b = pr.dump(), pr_h.dump()
+        for k in ("morton", "perm", "left", "right", "parent"):
+            np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+        np.testing.assert_array_equal(a["boxes"].view(np.uint32), b["boxes"].view(np.uint32))
+        assert pr.info()["max_depth"] == pr_h.info()["max_depth"] >= 22
+        assert pr.info()["stale_nodes"] == pr_h.info()["stale_nodes"]
+        f1 = ctx.render_host(h, w, pr, spp=spp)
+        f2 = ctx_h.render_host(h, w, pr_h, spp=spp)
+        assert_same(f1, f2, "1M spheres: warpqueue/device build vs mega/host build")
+        assert len(np.unique(f1)) > 1000
+
+
 def test_large_frame_properties(R):
     """irreg at 4000x4000 (BASELINE config 4's frame size) — too slow for the CPU oracle inside a test, so
     size-independent properties: all kernels agree bit-for-bit; sub-sampling the 4000^2 render at stride 4
