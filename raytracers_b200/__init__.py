@@ -32,7 +32,8 @@ class RayError(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libray_b200.so")
+    # RAY_B200_LIB: load another build of the same library (development A/B runs only)
+    return os.environ.get("RAY_B200_LIB") or os.path.join(_HERE, "libray_b200.so")
 
 
 class BvhInfo(C.Structure):

@@ -212,7 +212,7 @@ int fill_params(futhark_context *ctx, const futhark_opaque_prepared_scene *p, in
     for (int attempt = 0; attempt < 2; attempt++) {
       const bool pk = want_packet != 0;
       per_warp = (int64_t)wq_warp_bytes(k, wq_node_capacity(k, p->max_depth), pk);
-      wq_w = ctx->cfg.wq_warps < 1 ? 1 : (ctx->cfg.wq_warps > 24 ? 24 : ctx->cfg.wq_warps);
+      wq_w = ctx->cfg.wq_warps < 1 ? 1 : (ctx->cfg.wq_warps > kWqMaxWarps ? kWqMaxWarps : ctx->cfg.wq_warps);
       while (wq_w > 1 && wq_w * per_warp + 8192 > (int64_t)ctx->max_smem_optin) wq_w--;
       if (want_packet >= 0) break;
       const int64_t b = (int64_t)ctx->max_smem_optin - wq_w * per_warp - 512 - 128;

@@ -515,7 +515,7 @@ constexpr uint32_t kIndexMask = (1u << kSlotShift) - 1u;
 constexpr unsigned long long kNoHit = ~0ull;
 
 template <int K, bool kSpread, bool kPacket, bool kAllNodes, bool kSpheres>
-__global__ void __launch_bounds__(768, 1) render_warpqueue_kernel(const __grid_constant__ RenderParams P, const int ncap,
+__global__ void __launch_bounds__(kWqMaxThreads, 1) render_warpqueue_kernel(const __grid_constant__ RenderParams P, const int ncap,
                                                                    const int packet_min, const int refill_min) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const float4 *s_nodes, *s_geom;

@@ -77,6 +77,11 @@ void launch_detile(const int32_t *gathered, int32_t *out, int64_t H, int64_t W, 
 __host__ __device__ inline size_t staging_bytes(const RenderParams &p) {
   return 128 + (size_t)p.smem_nodes * 64 + (size_t)p.smem_spheres * 16;
 }
+#ifndef RAYB200_WQ_THREADS
+#define RAYB200_WQ_THREADS 768
+#endif
+constexpr int kWqMaxThreads = RAYB200_WQ_THREADS;  // warp-queue kernel: CTA size bound (one CTA per SM) -> register budget
+constexpr int kWqMaxWarps = kWqMaxThreads / 32;
 constexpr int kWqRing = 8;         // warp-queue kernel: pixels a warp may have open at once when samples are spread
 constexpr int kWqLeafStack = 128;  // warp-queue kernel: leaf-item stack (never more than 31 + 64 live)
 constexpr int kWqPacketStack = 64; // warp-queue kernel: deferred (node, mask) pairs of the packet walk (<= tree depth)
