@@ -37,7 +37,8 @@ enum ray_b200_kernel {
   RAY_B200_KERNEL_MEGA = 1,       /* one thread per pixel, whole ray_colour loop (parity anchor) */
   RAY_B200_KERNEL_PERSISTENT = 2, /* persistent CTAs, TMA-staged BVH, per-lane dynamic path refill */
   RAY_B200_KERNEL_WAVEFRONT = 3,  /* per-bounce persistent kernel + global ray queues + warp-vote compaction */
-  RAY_B200_KERNEL_WARPQUEUE = 4   /* persistent; lanes bound to (ray,node) items on warp-private smem queues */
+  RAY_B200_KERNEL_WARPQUEUE = 4,  /* persistent; lanes bound to (ray,node) items on warp-private smem queues */
+  RAY_B200_KERNEL_STREAMQUEUE = 5 /* the same without rounds: per-ray item counters, finished rays refilled continuously */
 };
 
 /* ---- context extensions ---------------------------------------------------------------------- */

@@ -24,7 +24,7 @@ __all__ = ["Context", "RayError", "lib_path", "load_library", "KERNELS", "declar
            "host_camera", "host_lbvh", "host_sample_offsets"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-KERNELS = {"auto": 0, "mega": 1, "persistent": 2, "wavefront": 3, "warpqueue": 4}
+KERNELS = {"auto": 0, "mega": 1, "persistent": 2, "wavefront": 3, "warpqueue": 4, "streamqueue": 5}
 
 
 class RayError(RuntimeError):

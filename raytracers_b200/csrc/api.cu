@@ -128,6 +128,7 @@ int parse_kernel(const char *v, int dflt) {
   if (!strcmp(v, "persistent")) return RAY_B200_KERNEL_PERSISTENT;
   if (!strcmp(v, "wavefront")) return RAY_B200_KERNEL_WAVEFRONT;
   if (!strcmp(v, "warpqueue")) return RAY_B200_KERNEL_WARPQUEUE;
+  if (!strcmp(v, "streamqueue")) return RAY_B200_KERNEL_STREAMQUEUE;
   return atoi(v);
 }
 
@@ -198,6 +199,16 @@ int fill_params(futhark_context *ctx, const futhark_opaque_prepared_scene *p, in
   // shared-memory staging plan: BFS prefix of the node array, then the sphere records if they all fit.
   // The warp-queue kernel runs one CTA per SM and gives the staging area whatever its queues leave.
   int64_t budget = std::min<int64_t>(ctx->cfg.smem_budget, ctx->max_smem_optin - 1024) - 128;
+  if (resolve_kernel(ctx) == RAY_B200_KERNEL_STREAMQUEUE) {
+    const int k = ctx->cfg.wq_k == 1 ? 1 : 2;
+    const int64_t per_warp = (int64_t)sq_warp_bytes(k, wq_node_capacity(k, p->max_depth));
+    int64_t wq_w = ctx->cfg.wq_warps < 1 ? 1 : (ctx->cfg.wq_warps > kWqMaxWarps ? kWqMaxWarps : ctx->cfg.wq_warps);
+    while (wq_w > 1 && wq_w * per_warp + 8192 > (int64_t)ctx->max_smem_optin) wq_w--;
+    budget = (int64_t)ctx->max_smem_optin - wq_w * per_warp - 512;
+    if (budget < 256) { set_error(ctx, "render: stream-queue kernel does not fit shared memory (tree depth %d)", p->max_depth); return 1; }
+    ctx->plan_wq_packet = 0;
+    ctx->plan_wq_warps = (int32_t)wq_w;
+  }
   if (resolve_kernel(ctx) == RAY_B200_KERNEL_WARPQUEUE) {
     // one CTA per SM: as many warps as asked for (<= 24) while their queues leave >= 8 KB for staging;
     // deep trees need bigger node stacks, so they get fewer warps
@@ -285,7 +296,7 @@ int do_render(futhark_context *ctx, RenderParams &P) {
   lc.wq_packet = ctx->plan_wq_packet;
   if (lc.kernel == RAY_B200_KERNEL_WAVEFRONT && ensure_wavefront(ctx, P.local_tiles * kTilePixels)) return 1;
   P.sample_buf = nullptr;
-  if (lc.kernel == RAY_B200_KERNEL_WARPQUEUE && P.spp > 1 && P.spp <= 65535 && ctx->cfg.wq_spread) {
+  if ((lc.kernel == RAY_B200_KERNEL_WARPQUEUE || lc.kernel == RAY_B200_KERNEL_STREAMQUEUE) && P.spp > 1 && P.spp <= 65535 && ctx->cfg.wq_spread) {
     // samples of a pixel are spread over a warp's slots; finished colours wait here for the in-order sum
     const size_t need = (size_t)lc.sm_count * lc.wq_warps * kWqRing * (size_t)P.spp * sizeof(float4);
     if (need > ctx->sample_buf_bytes) {
@@ -298,7 +309,7 @@ int do_render(futhark_context *ctx, RenderParams &P) {
     P.sample_buf = ctx->sample_buf;
   }
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev_start, ctx->stream));
-  if (lc.kernel == RAY_B200_KERNEL_PERSISTENT || lc.kernel == RAY_B200_KERNEL_WARPQUEUE)
+  if (lc.kernel == RAY_B200_KERNEL_PERSISTENT || lc.kernel == RAY_B200_KERNEL_WARPQUEUE || lc.kernel == RAY_B200_KERNEL_STREAMQUEUE)
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->work_cursor, 0, sizeof(int32_t), ctx->stream));
   launch_render(P, lc, &ctx->wf, ctx->stream, &ctx->launches);
   CUDA_TRY(ctx, cudaGetLastError());
@@ -936,7 +947,7 @@ int ray_b200_context_set_spp(struct futhark_context *ctx, int32_t spp) {
 }
 int ray_b200_context_set_kernel(struct futhark_context *ctx, int32_t k) {
   if (bad_ctx(ctx)) return 1;
-  if (k < RAY_B200_KERNEL_AUTO || k > RAY_B200_KERNEL_WARPQUEUE) { set_error(ctx, "unknown kernel %d", k); return 1; }
+  if (k < RAY_B200_KERNEL_AUTO || k > RAY_B200_KERNEL_STREAMQUEUE) { set_error(ctx, "unknown kernel %d", k); return 1; }
   ctx->cfg.kernel = k;
   return 0;
 }

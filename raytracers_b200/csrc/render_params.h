@@ -97,6 +97,13 @@ __host__ __device__ inline size_t wq_warp_bytes(int k, int ncap, bool packet) {
   const size_t r = 32 * (size_t)k;
   return ((r * (16 * 5 + 8 + 4) + 2 * kWqRing * 4 + (packet ? 2 * kWqPacketStack * 4 : 0) + kWqLeafStack * 4 + (size_t)ncap * 4) + 127) & ~(size_t)127;
 }
+// stream-queue kernel (K4): per-warp bytes (5 float4 + best + item + pending per slot, done/free lists, ring, stacks)
+__host__ __device__ inline size_t sq_warp_bytes(int k, int ncap) {
+  const size_t r = 32 * (size_t)k;
+  return ((r * (16 * 5 + 8 + 4 + 4 + 4 + 4) + 2 * kWqRing * 4 + kWqLeafStack * 4 + (size_t)ncap * 4) + 127) & ~(size_t)127;
+}
+
+
 cudaError_t configure_kernels(int max_dynamic_smem);
 
 }  // namespace rayb200

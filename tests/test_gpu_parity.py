@@ -10,7 +10,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-KERNELS = ["mega", "persistent", "wavefront", "warpqueue"]
+KERNELS = ["mega", "persistent", "wavefront", "warpqueue", "streamqueue"]
 
 
 def sha(a):
@@ -138,6 +138,31 @@ def test_warpqueue_packet_walk(R, oracle, golden, packet_min):
         assert_same(ctx.render_host(32, 48, pr), w4, f"packet {packet_min} two spheres")
 
 
+@pytest.mark.parametrize("tuning", [dict(wq_warps=24, wq_k=1), dict(wq_warps=5, wq_k=2, wq_refill=1), dict(wq_warps=16, wq_k=1, wq_refill=32),
+                                    dict(wq_warps=8, wq_k=2, wq_spread=0)])
+def test_streamqueue_variants(R, oracle, golden, tuning):
+    """K4 (continuous refill): reference PNG, partial tiles with spp > 1 (incl. the compact sharded layout), deep tree."""
+    import torch
+    from raytracers_b200 import distributed as D
+    want, _ = golden["rgbbox_500"]
+    assert_same(gpu_frame(R, "rgbbox", 500, 500, "streamqueue", **tuning), want, f"streamqueue {tuning} vs reference PNG")
+    h, w, spp = 45, 83, 5
+    w2, _, _ = oracle.Scene.irreg().prepare(h, w).render(h, w, spp=spp)
+    with R.Context(kernel="streamqueue", **tuning) as ctx:
+        pr = ctx.prepare_scene(h, w, ctx.irreg())
+        assert_same(ctx.render_host(h, w, pr, spp=spp), w2, f"streamqueue {tuning} spp 5")
+        world = 3
+        padded = D.tile_layout(h, w, world)[3]
+        for rank in range(world):
+            tiles = torch.empty((padded, 32), dtype=torch.int32, device="cuda")
+            ctx.set_shard(rank, world)
+            ctx.render_shard_into(tiles.data_ptr(), h, w, pr, spp=spp)
+            ctx.sync()
+            np.testing.assert_array_equal(tiles.cpu().numpy(), D.extract_rank_tiles(w2, rank, world))
+    w3, _, _ = oracle.render_scene("random", 64, 96, n=60000, seed=3)
+    assert_same(gpu_frame(R, "random", 64, 96, "streamqueue", n=60000, seed=3, **tuning), w3, f"streamqueue {tuning} deep tree")
+
+
 def test_warpqueue_deep_tree_and_many_samples(R, oracle):
     """Deep tree (bigger per-warp stacks -> fewer warps fit) and a sample count larger than one ring round."""
     n, h, w = 150000, 64, 96
@@ -160,7 +185,8 @@ def test_headline_config_64spp_kernels_agree(R):
         a = gpu_frame(R, name, 1000, 1000, "persistent", spp=64)
         b = gpu_frame(R, name, 1000, 1000, "warpqueue", spp=64)
         c = gpu_frame(R, name, 1000, 1000, "warpqueue", spp=64, wq_spread=0)
-        assert sha(a) == sha(b) == sha(c), name
+        d = gpu_frame(R, name, 1000, 1000, "streamqueue", spp=64)
+        assert sha(a) == sha(b) == sha(c) == sha(d), name
 
 
 def test_custom_scenes_edge_cases(R, oracle):

@@ -67,7 +67,7 @@ def main():
                 grid = [("x", "x", "x")]
             elif kernel == "wavefront":
                 grid = itertools.product(a.blocks_per_sm.split(","), a.tail_from.split(","), a.smem_budget.split(","))
-            elif kernel == "warpqueue":
+            elif kernel in ("warpqueue", "streamqueue"):
                 grid = itertools.product(a.wq_warps.split(","), a.wq_refill.split(","), a.wq_packet.split(","))
             else:
                 grid = itertools.product(a.blocks_per_sm.split(","), a.refill_min.split(","), a.smem_budget.split(","))
@@ -76,7 +76,7 @@ def main():
                     tuning = {}
                 elif kernel == "wavefront":
                     tuning = dict(blocks_per_sm=int(bps), tail_from=int(rf), smem_budget=int(sb))
-                elif kernel == "warpqueue":
+                elif kernel in ("warpqueue", "streamqueue"):
                     tuning = dict(wq_warps=int(bps), wq_refill=int(rf), wq_packet=int(sb))
                 else:
                     tuning = dict(blocks_per_sm=int(bps), refill_min=int(rf), smem_budget=int(sb))
