@@ -200,7 +200,7 @@ int fill_params(futhark_context *ctx, const futhark_opaque_prepared_scene *p, in
   // The warp-queue kernel runs one CTA per SM and gives the staging area whatever its queues leave.
   int64_t budget = std::min<int64_t>(ctx->cfg.smem_budget, ctx->max_smem_optin - 1024) - 128;
   if (resolve_kernel(ctx) == RAY_B200_KERNEL_STREAMQUEUE) {
-    const int k = ctx->cfg.wq_k == 1 ? 1 : 2;
+    const int k = 1;
     const int64_t per_warp = (int64_t)sq_warp_bytes(k, wq_node_capacity(k, p->max_depth));
     int64_t wq_w = ctx->cfg.wq_warps < 1 ? 1 : (ctx->cfg.wq_warps > kWqMaxWarps ? kWqMaxWarps : ctx->cfg.wq_warps);
     while (wq_w > 1 && wq_w * per_warp + 8192 > (int64_t)ctx->max_smem_optin) wq_w--;

@@ -943,7 +943,11 @@ __global__ void __launch_bounds__(kWqMaxThreads, 1) render_warpqueue_kernel(cons
 }
 
 // ====================================================================================== K4: stream queue
-// K3 without rounds.  In K3 a round of 32*K rays cannot end before its slowest ray has walked its ~15 dependent node
+// K3 without rounds — a measured NEGATIVE result, kept (like K2) as an alternative with parity tests: on B200 it is
+// ~50 % slower than K3 on every config (profiles/r1_sweep_streamqueue_vs_warpqueue.json); the per-item shared-memory
+// atomics on the ray counters (siblings of one ray sit next to each other in the LIFO, so they serialise), the done/free
+// lists and the sparser refill batches cost more than the round tails they remove.
+// In K3 a round of 32*K rays cannot end before its slowest ray has walked its ~15 dependent node
 // steps, so every round has a tail of partial batches (ncu: 25 of 32 lanes active).  K4 keeps the queues permanently
 // topped up instead: every ray carries a counter of its outstanding items in shared memory (+children -1 per node item,
 // -1 per leaf item); the lane that brings a counter to zero puts the ray on a "done" list; done rays are shaded in dense
@@ -1318,7 +1322,7 @@ cudaError_t configure_kernels(int max_dynamic_smem) {
   RAYB200_SET((render_streamqueue_kernel<KK, SP, true, false>));  \
   RAYB200_SET((render_streamqueue_kernel<KK, SP, false, true>));  \
   RAYB200_SET((render_streamqueue_kernel<KK, SP, false, false>));
-  RAYB200_SET_SQ(1, false) RAYB200_SET_SQ(1, true) RAYB200_SET_SQ(2, false) RAYB200_SET_SQ(2, true)
+  RAYB200_SET_SQ(1, false) RAYB200_SET_SQ(1, true)
 #undef RAYB200_SET_SQ
 #undef RAYB200_SET
   return cudaSuccess;
@@ -1356,8 +1360,8 @@ void launch_render(const RenderParams &p, const LaunchConfig &lc, const Wavefron
     }
     return;
   }
-  if (lc.kernel == 5) {  // RAY_B200_KERNEL_STREAMQUEUE: one CTA per SM, rays refilled continuously (no rounds)
-    const int k = lc.wq_k == 1 ? 1 : 2;
+  if (lc.kernel == 5) {  // RAY_B200_KERNEL_STREAMQUEUE: one CTA per SM, rays refilled continuously (no rounds); 32 rays per warp
+    const int k = 1;
     const int wthreads = 32 * lc.wq_warps;
     const int ncap = wq_node_capacity(k, p.max_depth);
     const size_t wsmem = ((staging_bytes(p) + 127) & ~(size_t)127) + (size_t)lc.wq_warps * sq_warp_bytes(k, ncap);
@@ -1373,8 +1377,7 @@ void launch_render(const RenderParams &p, const LaunchConfig &lc, const Wavefron
     else if (sph) RAYB200_SQ(KK, SP, false, true);                                        \
     else RAYB200_SQ(KK, SP, false, false);                                                \
   } while (0)
-    if (k == 1) { if (spread) RAYB200_SQ2(1, true); else RAYB200_SQ2(1, false); }
-    else { if (spread) RAYB200_SQ2(2, true); else RAYB200_SQ2(2, false); }
+    if (spread) RAYB200_SQ2(1, true); else RAYB200_SQ2(1, false);
 #undef RAYB200_SQ2
 #undef RAYB200_SQ
     (*launches)++;

@@ -138,8 +138,8 @@ def test_warpqueue_packet_walk(R, oracle, golden, packet_min):
         assert_same(ctx.render_host(32, 48, pr), w4, f"packet {packet_min} two spheres")
 
 
-@pytest.mark.parametrize("tuning", [dict(wq_warps=24, wq_k=1), dict(wq_warps=5, wq_k=2, wq_refill=1), dict(wq_warps=16, wq_k=1, wq_refill=32),
-                                    dict(wq_warps=8, wq_k=2, wq_spread=0)])
+@pytest.mark.parametrize("tuning", [dict(wq_warps=24), dict(wq_warps=5, wq_refill=1), dict(wq_warps=16, wq_refill=32),
+                                    dict(wq_warps=8, wq_spread=0)])
 def test_streamqueue_variants(R, oracle, golden, tuning):
     """K4 (continuous refill): reference PNG, partial tiles with spp > 1 (incl. the compact sharded layout), deep tree."""
     import torch
