@@ -226,12 +226,21 @@ def run_ours(args):
     sharded = D.ShardedRenderer(ctx, rank, world) if world > 1 else None
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
+    # One step = every frame of the workload, submitted as ONE batch (ray_b200_render_batch: two frames in flight, so
+    # the long-path tail of a frame is covered by the start of the next); the frame with the longest tail goes first.
+    order = sorted(SCENES, key=lambda n: n != "irreg")
+
     def step():
-        for name in SCENES:
-            if sharded is None:
-                ctx.render_into(frames[name].data_ptr(), H, W, prepared[name], spp=SPP)
-            else:
-                sharded.render(H, W, prepared[name], spp=SPP)
+        if args.no_batch:
+            for name in SCENES:
+                if sharded is None:
+                    ctx.render_into(frames[name].data_ptr(), H, W, prepared[name], spp=SPP)
+                else:
+                    sharded.render(H, W, prepared[name], spp=SPP)
+        elif sharded is None:
+            ctx.render_batch([dict(prepared=prepared[n], h=H, w=W, spp=SPP, out_dev=frames[n].data_ptr()) for n in order])
+        else:
+            sharded.render_batch([(H, W, prepared[n], SPP) for n in order])
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -398,6 +407,7 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "kernel": args.kernel, "spp": SPP, "segments_per_step": seg_per_step,
                        "l2": "flushed between timed steps (256 MiB memset outside the event pairs); scene is <1 MB",
                        "parallelism": f"tile-sharded x{world}, one NCCL gather per frame" if world > 1 else "single GPU",
+                       "submission": "frame by frame" if args.no_batch else "one ray_b200_render_batch per step (two frames in flight)",
                        "ray": "one ray segment = one objs_hit call (ray.fut:76-86)"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "frame_ms_1spp": one_spp, "extra": extra, "shard_kernel_ms_per_rank": rank_kernel_ms,
@@ -433,6 +443,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--kernel", default=os.environ.get("RAY_KERNEL", "auto"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-batch", action="store_true", help="submit the frames of a step one by one instead of as one batch")
     ap.add_argument("--extra", action="store_true",
                     help="also measure (once, outside the timed steps) BASELINE configs[3] and [4]: irreg 4000x4000 256spp and the 1M-sphere scene")
     ap.add_argument("--workload", default="headline", choices=sorted(WORKLOADS),

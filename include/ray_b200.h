@@ -56,6 +56,11 @@ int ray_b200_context_device(struct futhark_context *ctx);
 int ray_b200_context_last_render_ms(struct futhark_context *ctx, float *ms);
 /* Number of kernel launches issued by this context since creation. */
 int64_t ray_b200_context_launch_count(struct futhark_context *ctx);
+/* Diagnostic: while enabled, every warp of the warp-queue kernel records when it ran out of work.
+ * ray_b200_context_warp_trace returns, for the last traced render, each warp's exit time in microseconds after
+ * the first CTA started (exit_us may be NULL to query *count = SMs x warps per CTA).  Syncs the stream. */
+int ray_b200_context_trace_warps(struct futhark_context *ctx, int32_t enable);
+int ray_b200_context_warp_trace(struct futhark_context *ctx, float *exit_us, int64_t capacity, int64_t *count);
 
 /* ---- scenes ------------------------------------------------------------------------------------ */
 /* spheres: n x 7 floats (pos.xyz, colour.xyz, radius) — the `sphere` record of ray.fut:22-24;
@@ -118,6 +123,21 @@ int64_t ray_b200_shard_tiles_padded(int64_t h, int64_t w, int32_t world);
 /* Renders this rank's tiles into a compact tile-major device buffer int32[tiles_padded][32]. */
 int ray_b200_render_shard_into(struct futhark_context *ctx, int32_t *out_tiles_dev, int64_t h, int64_t w,
                                int32_t spp, const struct futhark_opaque_prepared_scene *p);
+/* Several frames in one call, up to two of them in flight on the device, so that the long-path tail of one frame
+ * is covered by the start of the next (the frames are independent: different prepared scenes, sizes or outputs).
+ * For the caller the batch is ONE operation on the context's stream: it starts after earlier work on that stream, and
+ * later work on that stream starts after every job has finished.  Jobs are launched in array order (put the frame
+ * with the longest tail first).  ray_b200_context_last_render_ms then reports the whole batch. */
+struct ray_b200_render_job {
+  const struct futhark_opaque_prepared_scene *prepared;
+  int64_t h, w;
+  int32_t spp;          /* 0 = the context's default */
+  int32_t shard_layout; /* 0: out_dev = int32[h][w], row-major (ray_b200_render_into);
+                           1: out_dev = this rank's compact tiles int32[tiles_padded][32] (ray_b200_render_shard_into) */
+  int32_t *out_dev;     /* device */
+  float *out_rgb_dev;   /* device float[h][w][3] or NULL (row-major layout only) */
+};
+int ray_b200_render_batch(struct futhark_context *ctx, const struct ray_b200_render_job *jobs, int32_t n);
 /* gathered_dev: int32[world][tiles_padded][32] (rank-major, as produced by an NCCL gather);
  * writes the row-major image int32[h][w] to out_pix_dev. */
 int ray_b200_detile(struct futhark_context *ctx, const int32_t *gathered_dev, int32_t *out_pix_dev, int64_t h,

@@ -50,6 +50,12 @@ class WorkCounters(C.Structure):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}
 
 
+class RenderJob(C.Structure):
+    """struct ray_b200_render_job (include/ray_b200.h)."""
+    _fields_ = [("prepared", C.c_void_p), ("h", C.c_int64), ("w", C.c_int64), ("spp", C.c_int32), ("shard_layout", C.c_int32),
+                ("out_dev", C.c_void_p), ("out_rgb_dev", C.c_void_p)]
+
+
 _lib = None
 
 
@@ -103,6 +109,9 @@ def load_library():
         "ray_b200_context_set_shard": (C.c_int, [vp, i32, i32]),
         "ray_b200_context_device": (C.c_int, [vp]),
         "ray_b200_context_last_render_ms": (C.c_int, [vp, C.POINTER(C.c_float)]),
+        "ray_b200_render_batch": (C.c_int, [vp, C.POINTER(RenderJob), C.c_int32]),
+        "ray_b200_context_trace_warps": (C.c_int, [vp, C.c_int32]),
+        "ray_b200_context_warp_trace": (C.c_int, [vp, C.POINTER(C.c_float), C.c_int64, C.POINTER(C.c_int64)]),
         "ray_b200_context_launch_count": (i64, [vp]),
         "ray_b200_scene_from_arrays": (C.c_int, [vp, pp, vp, i64, vp]),
         "ray_b200_scene_random": (C.c_int, [vp, pp, i64, u64]),
@@ -454,6 +463,18 @@ class Context:
         self._check(self.lib.ray_b200_context_last_render_ms(self.handle, C.byref(ms)))
         return float(ms.value)
 
+    def trace_warps(self, enable=True):
+        """Diagnostic: record when each warp of the warp-queue kernel runs out of work (see warp_trace)."""
+        self._check(self.lib.ray_b200_context_trace_warps(self.handle, 1 if enable else 0))
+
+    def warp_trace(self):
+        """float32[SMs * warps]: exit time of every warp of the last traced render, in us after the first CTA started."""
+        n = C.c_int64(0)
+        self._check(self.lib.ray_b200_context_warp_trace(self.handle, None, 0, C.byref(n)))
+        out = np.empty(n.value, np.float32)
+        self._check(self.lib.ray_b200_context_warp_trace(self.handle, out.ctypes.data_as(C.POINTER(C.c_float)), n.value, C.byref(n)))
+        return out
+
     def launch_count(self):
         return int(self.lib.ray_b200_context_launch_count(self.handle))
 
@@ -474,6 +495,19 @@ class Context:
 
     def render_shard_into(self, out_tiles_dev, h, w, prepared, spp=1):
         self._check(self.lib.ray_b200_render_shard_into(self.handle, _ptr(out_tiles_dev), int(h), int(w), int(spp), prepared.handle))
+
+    def render_batch(self, jobs):
+        """jobs: sequence of dicts(prepared=, h=, w=, out_dev=, spp=0, shard_layout=False, out_rgb_dev=None).  Enqueues all
+        frames as one stream-ordered operation with up to two of them in flight (ray_b200_render_batch)."""
+        arr = (RenderJob * len(jobs))()
+        for a, j in zip(arr, jobs):
+            a.prepared = j["prepared"].handle
+            a.h, a.w = int(j["h"]), int(j["w"])
+            a.spp = int(j.get("spp") or 0)
+            a.shard_layout = 1 if j.get("shard_layout") else 0
+            a.out_dev = int(j["out_dev"])
+            a.out_rgb_dev = int(j["out_rgb_dev"]) if j.get("out_rgb_dev") is not None else None
+        self._check(self.lib.ray_b200_render_batch(self.handle, arr, len(jobs)))
 
     def detile(self, gathered_dev, out_pix_dev, h, w, world):
         self._check(self.lib.ray_b200_detile(self.handle, _ptr(gathered_dev), _ptr(out_pix_dev), int(h), int(w), int(world)))

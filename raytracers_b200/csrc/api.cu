@@ -30,6 +30,8 @@ struct futhark_context_config {
   int32_t gpus = 1;  // > 1: this ONE process drives that many devices (RAY_GPUS; the drop-in multi-GPU mode of main.c)
   int32_t blocks_per_sm = 4, smem_budget = 48 * 1024, refill_min = 8, tail_from = 8;
   int32_t wq_warps = 24, wq_k = 1, wq_spread = 1, wq_packet = -1, wq_refill = 1, permute = 1, host_build = 0;
+  int32_t heavy_first = -1;  // pull long-path tiles to the front of the claim order: 0 off, 1/2/4 = probe pixels per tile, -1 = decide per frame
+  int32_t probe_segments = 8;
   std::string cache_file;
 };
 
@@ -42,8 +44,9 @@ struct futhark_context {
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
   bool have_timing = false;
   int sm_count = 0, max_smem_optin = 0;
-  int32_t *work_cursor = nullptr;           // device
   unsigned long long *counters = nullptr;   // device [4]
+  unsigned long long *warp_trace = nullptr; // device [1 + SMs * kWqMaxWarps] when tracing is on (ray_b200_context_trace_warps)
+  int trace_warps = 0;                      // warps per CTA of the last traced launch
   float *offsets = nullptr;                 // device sample-offset table
   int32_t offsets_spp = 0;
   int64_t launches = 0;
@@ -60,8 +63,18 @@ struct futhark_context {
   cudaEvent_t peer_done = nullptr;      // helper context: its shard has been rendered
   int32_t *gathered = nullptr;          // rank 0: [gpus][tiles_padded][32] staging for the de-tiling kernel (grow-only)
   size_t gathered_bytes = 0;                // warps per CTA the warp-queue kernel will use for the frame being set up
-  float4 *sample_buf = nullptr;             // warp-queue kernel, spp > 1: per-warp finished-sample colours
-  size_t sample_buf_bytes = 0;
+  // Per-render scratch.  Lane 0 runs on the context's stream; lane 1 (own stream, created on first use) lets
+  // ray_b200_render_batch keep two frames in flight so that one frame's tail is covered by the next frame's start.
+  struct Lane {
+    cudaStream_t stream = nullptr;             // lane 0: mirrors ctx->stream at each use
+    int32_t *work_cursor = nullptr;            // device
+    float4 *sample_buf = nullptr;              // warp-queue kernel, spp > 1: per-warp finished-sample colours
+    size_t sample_buf_bytes = 0;
+    unsigned char *tile_order_block = nullptr; // heavy-first claim order: keys, sorted keys, ids, order, cub temp (one allocation)
+    size_t tile_order_bytes = 0;
+    TileOrderBuffers tile_order_plan{};
+  } lanes[2];
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool profiling_paused = false;
   int64_t renders = 0;
   bool ok = false;
@@ -132,7 +145,7 @@ int parse_kernel(const char *v, int dflt) {
   return atoi(v);
 }
 
-const char *kTuningNames[] = {"kernel", "spp", "blocks_per_sm", "smem_budget", "refill_min", "tail_from", "wq_warps", "wq_k", "wq_spread", "wq_packet", "wq_refill", "permute", "host_build", "rank", "world", "gpus"};
+const char *kTuningNames[] = {"kernel", "spp", "blocks_per_sm", "smem_budget", "refill_min", "tail_from", "wq_warps", "wq_k", "wq_spread", "wq_packet", "wq_refill", "permute", "heavy_first", "probe_segments", "host_build", "rank", "world", "gpus"};
 constexpr int kNumTuning = sizeof(kTuningNames) / sizeof(kTuningNames[0]);
 
 bool bad_ctx(futhark_context *ctx) { return ctx == nullptr || !ctx->ok; }
@@ -193,9 +206,19 @@ int fill_params(futhark_context *ctx, const futhark_opaque_prepared_scene *p, in
     P.chunk_stride = (int32_t)(P.n_chunks > 1 ? st % P.n_chunks : 0);
     if (P.n_chunks > 1 && P.chunk_stride == 0) P.chunk_stride = 1;
     if (!ctx->cfg.permute) { P.chunk_stride = 1; }
+    // modular inverse (extended Euclid): tile chunk q is claimed at position q * inv mod n_chunks (heavy-first order)
+    int64_t r0 = P.n_chunks, r1 = P.chunk_stride, t0 = 0, t1 = 1;
+    while (r1 != 0) {
+      const int64_t qd = r0 / r1, r2 = r0 - qd * r1, t2 = t0 - qd * t1;
+      r0 = r1; r1 = r2; t0 = t1; t1 = t2;
+    }
+    P.chunk_stride_inv = P.n_chunks > 1 ? (int32_t)(((t0 % P.n_chunks) + P.n_chunks) % P.n_chunks) : 0;
   }
-  P.work_cursor = ctx->work_cursor;
+  P.probes_per_tile = 1; P.probe_segments = 8;
+  P.work_cursor = nullptr;  // the lane's, set by do_render
   P.counters = ctx->counters;
+  P.warp_trace = nullptr;
+  P.tile_order = nullptr;
   // shared-memory staging plan: BFS prefix of the node array, then the sphere records if they all fit.
   // The warp-queue kernel runs one CTA per SM and gives the staging area whatever its queues leave.
   int64_t budget = std::min<int64_t>(ctx->cfg.smem_budget, ctx->max_smem_optin - 1024) - 128;
@@ -282,7 +305,10 @@ int ensure_wavefront(futhark_context *ctx, int64_t items) {
   return 0;
 }
 
-int do_render(futhark_context *ctx, RenderParams &P) {
+// Enqueues one frame on lane `lane_id` (0 = the context's stream).  `timed`: bracket it with the context's timing events.
+int do_render(futhark_context *ctx, RenderParams &P, int lane_id = 0, bool timed = true) {
+  futhark_context::Lane &L = ctx->lanes[lane_id];
+  if (lane_id == 0) L.stream = ctx->stream;
   LaunchConfig lc;
   lc.kernel = resolve_kernel(ctx);
   lc.blocks_per_sm = ctx->cfg.blocks_per_sm;
@@ -299,22 +325,61 @@ int do_render(futhark_context *ctx, RenderParams &P) {
   if ((lc.kernel == RAY_B200_KERNEL_WARPQUEUE || lc.kernel == RAY_B200_KERNEL_STREAMQUEUE) && P.spp > 1 && P.spp <= 65535 && ctx->cfg.wq_spread) {
     // samples of a pixel are spread over a warp's slots; finished colours wait here for the in-order sum
     const size_t need = (size_t)lc.sm_count * lc.wq_warps * kWqRing * (size_t)P.spp * sizeof(float4);
-    if (need > ctx->sample_buf_bytes) {
-      CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-      if (ctx->sample_buf) CUDA_TRY(ctx, cudaFree(ctx->sample_buf));
-      ctx->sample_buf = nullptr; ctx->sample_buf_bytes = 0;
-      CUDA_TRY(ctx, cudaMalloc(&ctx->sample_buf, need));
-      ctx->sample_buf_bytes = need;
+    if (need > L.sample_buf_bytes) {
+      CUDA_TRY(ctx, cudaStreamSynchronize(L.stream));
+      if (L.sample_buf) CUDA_TRY(ctx, cudaFree(L.sample_buf));
+      L.sample_buf = nullptr; L.sample_buf_bytes = 0;
+      CUDA_TRY(ctx, cudaMalloc(&L.sample_buf, need));
+      L.sample_buf_bytes = need;
     }
-    P.sample_buf = ctx->sample_buf;
+    P.sample_buf = L.sample_buf;
   }
-  CUDA_TRY(ctx, cudaEventRecord(ctx->ev_start, ctx->stream));
+  // heavy-first claim order (warp-queue kernel): worth its probe pass when a frame is long enough to have a tail to lose
+  // — more than one sample per pixel — and pointless when every tile is claimed in the first wave anyway
+  const int hf = ctx->cfg.heavy_first;
+  const bool heavy_first = lc.kernel == RAY_B200_KERNEL_WARPQUEUE && P.local_tiles > 1 && P.local_tiles < (1ll << 26) &&
+                           (hf > 0 || (hf < 0 && P.spp > 1));
+  if (heavy_first) {
+    P.probes_per_tile = hf >= 4 ? 4 : (hf >= 2 ? 2 : 1);
+    P.probe_segments = std::min(std::max(ctx->cfg.probe_segments, 1), kMaxDepth);
+    const size_t n = (size_t)P.local_tiles, tmp = tile_order_sort_bytes(P.local_tiles);
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t need = 4 * up(4 * n) + up(tmp);
+    if (need > L.tile_order_bytes) {
+      CUDA_TRY(ctx, cudaStreamSynchronize(L.stream));
+      if (L.tile_order_block) CUDA_TRY(ctx, cudaFree(L.tile_order_block));
+      L.tile_order_block = nullptr; L.tile_order_bytes = 0;
+      CUDA_TRY(ctx, cudaMalloc(&L.tile_order_block, need));
+      L.tile_order_bytes = need;
+    }
+    TileOrderBuffers tb;
+    unsigned char *q = L.tile_order_block;
+    tb.keys = reinterpret_cast<uint32_t *>(q); q += up(4 * n);
+    tb.keys_sorted = reinterpret_cast<uint32_t *>(q); q += up(4 * n);
+    tb.ids = reinterpret_cast<int32_t *>(q); q += up(4 * n);
+    tb.order = reinterpret_cast<int32_t *>(q); q += up(4 * n);
+    tb.sort_tmp = q; tb.sort_tmp_bytes = tmp;
+    P.tile_order = tb.order;
+    L.tile_order_plan = tb;
+  }
+  P.work_cursor = L.work_cursor;
+  if (ctx->warp_trace && lc.kernel == RAY_B200_KERNEL_WARPQUEUE && lane_id == 0) {
+    const size_t n = 1 + (size_t)lc.sm_count * kWqMaxWarps;
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->warp_trace, 0, n * sizeof(unsigned long long), L.stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->warp_trace, 0xff, sizeof(unsigned long long), L.stream));
+    P.warp_trace = ctx->warp_trace;
+    ctx->trace_warps = lc.wq_warps;
+  }
+  if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_start, L.stream));
   if (lc.kernel == RAY_B200_KERNEL_PERSISTENT || lc.kernel == RAY_B200_KERNEL_WARPQUEUE || lc.kernel == RAY_B200_KERNEL_STREAMQUEUE)
-    CUDA_TRY(ctx, cudaMemsetAsync(ctx->work_cursor, 0, sizeof(int32_t), ctx->stream));
-  launch_render(P, lc, &ctx->wf, ctx->stream, &ctx->launches);
+    CUDA_TRY(ctx, cudaMemsetAsync(L.work_cursor, 0, sizeof(int32_t), L.stream));
+  if (heavy_first) launch_tile_order(P, L.tile_order_plan, L.stream, &ctx->launches);
+  launch_render(P, lc, &ctx->wf, L.stream, &ctx->launches);
   CUDA_TRY(ctx, cudaGetLastError());
-  CUDA_TRY(ctx, cudaEventRecord(ctx->ev_stop, ctx->stream));
-  ctx->have_timing = true;
+  if (timed) {
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_stop, L.stream));
+    ctx->have_timing = true;
+  }
   ctx->renders++;
   return 0;
 }
@@ -479,6 +544,8 @@ int futhark_context_config_set_tuning_param(struct futhark_context_config *cfg, 
   else if (!strcmp(name, "wq_refill")) cfg->wq_refill = (int32_t)v;
   else if (!strcmp(name, "wq_packet")) cfg->wq_packet = (int32_t)v;  // (size_t)-1 = decide per scene
   else if (!strcmp(name, "permute")) cfg->permute = (int32_t)v;
+  else if (!strcmp(name, "heavy_first")) cfg->heavy_first = (int32_t)v;  // (size_t)-1 = decide per frame
+  else if (!strcmp(name, "probe_segments")) cfg->probe_segments = (int32_t)v;
   else if (!strcmp(name, "host_build")) cfg->host_build = (int32_t)v;
   else if (!strcmp(name, "rank")) cfg->rank = (int32_t)v;
   else if (!strcmp(name, "world")) cfg->world = (int32_t)v;
@@ -509,6 +576,8 @@ struct futhark_context *futhark_context_new(struct futhark_context_config *cfg) 
   ctx->cfg.wq_packet = env_int("RAY_WQ_PACKET", ctx->cfg.wq_packet);
   ctx->cfg.wq_refill = env_int("RAY_WQ_REFILL", ctx->cfg.wq_refill);
   ctx->cfg.permute = env_int("RAY_PERMUTE", ctx->cfg.permute);
+  ctx->cfg.heavy_first = env_int("RAY_HEAVY_FIRST", ctx->cfg.heavy_first);
+  ctx->cfg.probe_segments = env_int("RAY_PROBE_SEGMENTS", ctx->cfg.probe_segments);
   ctx->cfg.host_build = env_int("RAY_HOST_BUILD", ctx->cfg.host_build);
   ctx->cfg.debugging = env_int("RAY_DEBUG", ctx->cfg.debugging);
   memset(&ctx->wf, 0, sizeof ctx->wf);
@@ -535,7 +604,9 @@ struct futhark_context *futhark_context_new(struct futhark_context_config *cfg) 
   ctx->stream = ctx->own_stream;
   if ((e = cudaEventCreate(&ctx->ev_start)) != cudaSuccess) return fail("cudaEventCreate", e);
   if ((e = cudaEventCreate(&ctx->ev_stop)) != cudaSuccess) return fail("cudaEventCreate", e);
-  if ((e = cudaMalloc(&ctx->work_cursor, 64)) != cudaSuccess) return fail("cudaMalloc", e);
+  if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+  if ((e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+  if ((e = cudaMalloc(&ctx->lanes[0].work_cursor, 64)) != cudaSuccess) return fail("cudaMalloc", e);
   if ((e = cudaMalloc(&ctx->counters, 4 * sizeof(unsigned long long))) != cudaSuccess) return fail("cudaMalloc", e);
   if ((e = cudaMalloc(&ctx->d_build_result, sizeof(BvhBuildResult))) != cudaSuccess) return fail("cudaMalloc", e);
   if ((e = cudaMallocHost(&ctx->h_build_result, sizeof(BvhBuildResult))) != cudaSuccess) return fail("cudaMallocHost", e);
@@ -620,10 +691,17 @@ void futhark_context_free(struct futhark_context *ctx) {
   }
   for (auto &b : ctx->pinned_cache) { cudaEventDestroy(b.last_use); cudaFreeHost(b.ptr); }
   if (ctx->ok) free_wavefront(ctx);
-  if (ctx->sample_buf) cudaFree(ctx->sample_buf);
+  for (auto &L : ctx->lanes) {
+    if (L.sample_buf) cudaFree(L.sample_buf);
+    if (L.tile_order_block) cudaFree(L.tile_order_block);
+    if (L.work_cursor) cudaFree(L.work_cursor);
+  }
+  if (ctx->lanes[1].stream) cudaStreamDestroy(ctx->lanes[1].stream);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->offsets) cudaFree(ctx->offsets);
-  if (ctx->work_cursor) cudaFree(ctx->work_cursor);
   if (ctx->counters) cudaFree(ctx->counters);
+  if (ctx->warp_trace) cudaFree(ctx->warp_trace);
   if (ctx->d_build_result) cudaFree(ctx->d_build_result);
   if (ctx->h_build_result) cudaFreeHost(ctx->h_build_result);
   if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
@@ -969,6 +1047,35 @@ int ray_b200_context_last_render_ms(struct futhark_context *ctx, float *ms) {
 }
 int64_t ray_b200_context_launch_count(struct futhark_context *ctx) { return ctx ? ctx->launches : 0; }
 
+int ray_b200_context_trace_warps(struct futhark_context *ctx, int32_t enable) {
+  if (bad_ctx(ctx)) return 1;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  cudaSetDevice(ctx->cfg.device);
+  if (enable && !ctx->warp_trace) {
+    CUDA_TRY(ctx, cudaMalloc(&ctx->warp_trace, (1 + (size_t)ctx->sm_count * kWqMaxWarps) * sizeof(unsigned long long)));
+  } else if (!enable && ctx->warp_trace) {
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, cudaFree(ctx->warp_trace));
+    ctx->warp_trace = nullptr;
+  }
+  return 0;
+}
+int ray_b200_context_warp_trace(struct futhark_context *ctx, float *exit_us, int64_t capacity, int64_t *count) {
+  if (bad_ctx(ctx) || !count) return 1;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  cudaSetDevice(ctx->cfg.device);
+  if (!ctx->warp_trace || ctx->trace_warps == 0) { set_error(ctx, "warp_trace: no traced warp-queue render yet"); return 1; }
+  const int64_t n = (int64_t)ctx->sm_count * ctx->trace_warps;
+  *count = n;
+  if (!exit_us) return 0;
+  if (capacity < n) { set_error(ctx, "warp_trace: capacity %lld < %lld", (long long)capacity, (long long)n); return 1; }
+  std::vector<unsigned long long> h(1 + (size_t)n);
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpy(h.data(), ctx->warp_trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  for (int64_t i = 0; i < n; i++) exit_us[i] = h[1 + i] > h[0] ? (float)((double)(h[1 + i] - h[0]) * 1e-3) : 0.0f;
+  return 0;
+}
+
 int ray_b200_scene_from_arrays(struct futhark_context *ctx, struct futhark_opaque_scene **out0, const float *spheres, int64_t n,
                                const float *cam7) {
   if (bad_ctx(ctx)) return 1;
@@ -1119,6 +1226,68 @@ int ray_b200_render_shard_into(struct futhark_context *ctx, int32_t *out_tiles_d
     CUDA_TRY(ctx, cudaMemsetAsync(out_tiles_dev + P.local_tiles * kTilePixels, 0, (size_t)(padded - P.local_tiles) * kTilePixels * 4, ctx->stream));
   return do_render(ctx, P);
 }
+// Several frames in one call, up to two of them in flight: job i runs on lane i % 2, lane 1 forks from the context's
+// stream at the start of the call and joins it at the end, so for the caller the batch behaves like one stream-ordered
+// operation.  Why: a frame ends on its longest paths (a 50-bounce path is ~50 dependent traversals) while most SMs are
+// already idle; the persistent kernel of the NEXT frame cannot start there before the stream order lets it.  With the
+// second lane its CTAs take over every SM the moment the previous frame's CTA retires.
+int ray_b200_render_batch(struct futhark_context *ctx, const struct ray_b200_render_job *jobs, int32_t n) {
+  if (bad_ctx(ctx)) return 1;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (n < 0 || (n > 0 && !jobs)) { set_error(ctx, "render_batch: bad arguments"); return 1; }
+  if (n == 0) return 0;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  for (int32_t i = 0; i < n; i++) {
+    if (!jobs[i].out_dev) { set_error(ctx, "render_batch: job %d has no output buffer", i); return 1; }
+    if (jobs[i].shard_layout && jobs[i].out_rgb_dev) { set_error(ctx, "render_batch: job %d: no float output in the shard layout", i); return 1; }
+  }
+  const int kernel = resolve_kernel(ctx);
+  // the wavefront kernel's ray queues and the warp trace exist once per context: those batches run in order on lane 0
+  const bool two_lanes = n > 1 && kernel != RAY_B200_KERNEL_WAVEFRONT && !ctx->warp_trace;
+  futhark_context::Lane &L1 = ctx->lanes[1];
+  if (two_lanes && !L1.stream) {
+    CUDA_TRY(ctx, cudaStreamCreateWithFlags(&L1.stream, cudaStreamNonBlocking));
+    CUDA_TRY(ctx, cudaMalloc(&L1.work_cursor, 64));
+  }
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev_start, ctx->stream));
+  if (two_lanes) {
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(L1.stream, ctx->ev_fork, 0));
+  }
+  int rc = 0;
+  for (int32_t i = 0; i < n && !rc; i++) {
+    const ray_b200_render_job &j = jobs[i];
+    const int lane = two_lanes ? (i & 1) : 0;
+    const int32_t spp = j.spp > 0 ? j.spp : ctx->cfg.spp;
+    RenderParams P;
+    if (j.shard_layout) {
+      rc = fill_params(ctx, j.prepared, j.h, j.w, spp, ctx->cfg.rank, ctx->cfg.world, j.out_dev, nullptr, true, P);
+      const int64_t padded = rc ? 0 : ray_b200_shard_tiles_padded(j.h, j.w, ctx->cfg.world);
+      if (!rc && P.local_tiles < padded &&
+          cudaMemsetAsync(j.out_dev + P.local_tiles * kTilePixels, 0, (size_t)(padded - P.local_tiles) * kTilePixels * 4,
+                          lane ? L1.stream : ctx->stream) != cudaSuccess) {
+        set_error(ctx, "render_batch: memset failed");
+        rc = 1;
+      }
+    } else {
+      rc = fill_params(ctx, j.prepared, j.h, j.w, spp, ctx->cfg.rank, ctx->cfg.world, j.out_dev, j.out_rgb_dev, false, P);
+    }
+    if (!rc) rc = do_render(ctx, P, lane, false);
+  }
+  // join even after a failure: whatever was enqueued on lane 1 must be ordered before later work on the context's stream
+  if (two_lanes) {
+    if (cudaEventRecord(ctx->ev_join, L1.stream) != cudaSuccess || cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0) != cudaSuccess) {
+      if (!rc) set_error(ctx, "render_batch: join failed");
+      rc = 1;
+    }
+  }
+  if (!rc) {
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_stop, ctx->stream));
+    ctx->have_timing = true;
+  }
+  return rc;
+}
+
 int ray_b200_detile(struct futhark_context *ctx, const int32_t *gathered_dev, int32_t *out_pix_dev, int64_t h, int64_t w, int32_t world) {
   if (bad_ctx(ctx)) return 1;
   std::lock_guard<std::mutex> g(ctx->mu);

@@ -10,6 +10,7 @@
 // tests both children's boxes, ~half the dependent steps of the reference loop and no re-visits.
 // See find_closest for how leaf tests are decoupled from the walk and how ties are broken.
 #include "render_params.h"
+#include <cub/cub.cuh>
 #include "device_math.cuh"
 
 #include <cstdio>
@@ -199,8 +200,18 @@ __device__ __forceinline__ bool item_pixel(const RenderParams &P, int k, int &i,
   return t < P.n_tiles && i < P.W && j < P.H;
 }
 
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 // claim index (value of the global work cursor) -> item index: chunks of 64 tiles in stride-permuted order
 __device__ __forceinline__ int claim_to_item(const RenderParams &P, int c) {
+  if (P.tile_order) {  // heavy-first order from the probe pass
+    const int lt = c >> 5;
+    return lt < P.local_tiles ? (__ldg(P.tile_order + lt) << 5) | (c & 31) : (int)(P.local_tiles << 5);
+  }
   const int chunk = c >> 11;
   const int perm = (int)(((long long)chunk * P.chunk_stride) % P.n_chunks);
   return (perm << 11) | (c & 2047);
@@ -256,6 +267,47 @@ __global__ void __launch_bounds__(128) render_mega_kernel(const __grid_constant_
     P.out_pix[k64] = 0;  // padding pixel of a partial tile
   }
   if (kCount) flush_counters(P, wc);
+}
+
+// ====================================================================================== heavy-first claim order
+// The persistent kernels end a frame on whatever was claimed last; a 50-bounce path claimed late keeps one warp busy
+// for ~50 dependent traversals while the other SMs idle (profiles/r1_trace_tail.json: 44 % of the SM time of an
+// irreg 1/8 shard at 64 spp).  Sorting the tiles longest-first cures the tail but un-mixes the frame — first every
+// warp waits on L2 for deep nodes, then every warp shades sky — and the bulk gets 20 % slower.  So the claim order
+// stays the chunk permutation, and only the tiles whose probe path is still alive after `probe_segments` segments
+// ("heavy": possibly 50 bounces) are pulled into its first half: key = position in the permuted sequence, halved for
+// heavy tiles, stable-sorted.  What is claimed in the second half ends within probe_segments traversals.  The probe
+// traces sample 0 of 1, 2 or 4 pixels per 8x4 tile, so its own latency is bounded by the same cap.  The order only
+// changes WHEN a pixel is rendered, never its value.
+__global__ void __launch_bounds__(256) tile_probe_kernel(const __grid_constant__ RenderParams P, uint32_t *__restrict__ keys,
+                                                         int32_t *__restrict__ ids) {
+  const int probes = P.probes_per_tile;  // 1, 2 or 4: the lanes of a tile are neighbours in a warp
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long lt = t / probes;
+  const int q = (int)(t - lt * probes);
+  bool alive = false;
+  if (lt < P.local_tiles) {
+    const int sub = q == 0 ? 11 : (q == 1 ? 22 : (q == 2 ? 17 : 5));  // pixels (3,1) (6,2) (1,2) (5,0) of the tile
+    int i, j;
+    if (item_pixel(P, (int)(lt << 5) | sub, i, j)) {
+      const GlobalScene sc{P.nodes, P.geom};
+      Ray r = primary_ray(P, i, j, 0);
+      V3 light = v3(1.0f, 1.0f, 1.0f), colour;
+      int depth = 0, segments = 0;
+      WorkCounters wc;
+      do {
+        alive = advance_path<false>(sc, P, r, light, depth, colour, wc);
+      } while (alive && ++segments < P.probe_segments);
+    }
+  }
+  if (probes > 1) alive |= __shfl_xor_sync(kFullMask, alive, 1);
+  if (probes > 2) alive |= __shfl_xor_sync(kFullMask, alive, 2);
+  if (q == 0 && lt < P.local_tiles) {
+    const long long chunk = lt >> 6;
+    const uint32_t pos = (uint32_t)((chunk * P.chunk_stride_inv) % P.n_chunks) << 6 | (uint32_t)(lt & 63);
+    keys[lt] = alive ? pos >> 1 : pos;
+    ids[lt] = (int32_t)lt;
+  }
 }
 
 // ====================================================================================== TMA staging helpers
@@ -518,6 +570,7 @@ template <int K, bool kSpread, bool kPacket, bool kAllNodes, bool kSpheres>
 __global__ void __launch_bounds__(kWqMaxThreads, 1) render_warpqueue_kernel(const __grid_constant__ RenderParams P, const int ncap,
                                                                    const int packet_min, const int refill_min) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  if (P.warp_trace && threadIdx.x == 0) atomicMin(P.warp_trace, global_timer_ns());
   const float4 *s_nodes, *s_geom;
   stage_scene(P, smem_raw, s_nodes, s_geom);
   const StagedScene<kAllNodes, kSpheres> sc{P.nodes, P.geom, s_nodes, s_geom, P.smem_nodes};
@@ -747,6 +800,7 @@ __global__ void __launch_bounds__(kWqMaxThreads, 1) render_warpqueue_kernel(cons
       const bool undispensed = kSpread && (open_seq - disp_seq) * spp - disp_s > 0;
       if (exhausted && !undispensed && !__any_sync(kFullMask, any_active)) {
         if (kSpread) finalize_pixels();
+        if (P.warp_trace && lane == 0) P.warp_trace[1 + blockIdx.x * (blockDim.x >> 5) + warp] = global_timer_ns();
         break;                                                      // frame done for this warp
       }
       continue;                                                     // only sky / padding so far: hand out more
@@ -1423,6 +1477,22 @@ void launch_render(const RenderParams &p, const LaunchConfig &lc, const Wavefron
   else if (sph) render_persistent_kernel<false, true><<<(unsigned)want, threads, smem, stream>>>(p, refill);
   else render_persistent_kernel<false, false><<<(unsigned)want, threads, smem, stream>>>(p, refill);
   (*launches)++;
+}
+
+size_t tile_order_sort_bytes(int64_t local_tiles) {
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const int32_t *)nullptr,
+                                  (int32_t *)nullptr, (int)local_tiles, 0, 32);
+  return bytes;
+}
+
+void launch_tile_order(const RenderParams &p, const TileOrderBuffers &b, cudaStream_t stream, int64_t *launches) {
+  const long long threads = (long long)p.local_tiles * p.probes_per_tile;
+  tile_probe_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(p, b.keys, b.ids);
+  size_t bytes = b.sort_tmp_bytes;
+  cub::DeviceRadixSort::SortPairs(b.sort_tmp, bytes, b.keys, b.keys_sorted, b.ids, b.order, (int)p.local_tiles, 0,
+                                  tile_order_key_bits(p.n_chunks), stream);
+  if (launches) *launches += 2;  // the cub sort is counted as one
 }
 
 void launch_count_work(const RenderParams &p, cudaStream_t stream, int64_t *launches) {

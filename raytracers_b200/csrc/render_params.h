@@ -37,10 +37,18 @@ struct RenderParams {
   // chunk order is a stride permutation (chunk * chunk_stride mod n_chunks, stride coprime to n_chunks), so
   // the cheap sky and the 50-bounce ground of a frame are interleaved instead of the heavy rows coming last
   int32_t n_chunks, chunk_stride;
+  // heavy-first claim order (NULL = the chunk permutation above): the same permuted sequence, except that tiles whose
+  // probe path is long are pulled into its first half, so that a frame never ends on a 50-bounce path claimed late
+  const int32_t *tile_order;
+  int32_t chunk_stride_inv;  // chunk_stride * chunk_stride_inv = 1 (mod n_chunks): position of a tile chunk in the claim sequence
+  int32_t probes_per_tile, probe_segments;
   float4 *sample_buf;    // warp-queue kernel, spp > 1: [CTAs][warps][kWqRing][spp] finished-sample colours (else NULL)
   // persistent-threads work cursor and optional work counters
   int32_t *work_cursor;
   unsigned long long *counters;  // [4] segments, node_steps, box_tests, leaf_tests (counting kernels only)
+  // diagnostic (NULL unless tracing): [0] = earliest CTA start, [1 + cta * warps + warp] = that warp's exit, in
+  // %globaltimer ns — shows how long the SMs sit idle behind the frame's last paths (warp-queue kernel only)
+  unsigned long long *warp_trace;
 };
 
 // Wavefront ray queues (SoA in HBM, 48 B per live ray): two ping-pong queues indexed by bounce parity.
@@ -70,6 +78,20 @@ struct LaunchConfig {
 
 void launch_render(const RenderParams &p, const LaunchConfig &lc, const WavefrontBuffers *wf, cudaStream_t stream,
                    int64_t *launches);
+// Probe pass + sort that produce RenderParams::tile_order (see render_kernels.cu).  All buffers are device memory.
+struct TileOrderBuffers {
+  uint32_t *keys, *keys_sorted;   // [local_tiles]
+  int32_t *ids, *order;           // [local_tiles]
+  void *sort_tmp;
+  size_t sort_tmp_bytes;
+};
+size_t tile_order_sort_bytes(int64_t local_tiles);
+inline int tile_order_key_bits(int32_t n_chunks) {  // keys are positions < n_chunks * 64
+  int bits = 6;
+  while (bits < 32 && (1ll << bits) < (long long)n_chunks * 64) bits++;
+  return bits;
+}
+void launch_tile_order(const RenderParams &p, const TileOrderBuffers &b, cudaStream_t stream, int64_t *launches);
 void launch_count_work(const RenderParams &p, cudaStream_t stream, int64_t *launches);
 void launch_detile(const int32_t *gathered, int32_t *out, int64_t H, int64_t W, int32_t world, int64_t tiles_padded,
                    cudaStream_t stream, int64_t *launches);

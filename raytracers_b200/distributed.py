@@ -85,6 +85,7 @@ class ShardedRenderer:
         self._tiles = None
         self._frame = None
         self._key = None
+        self._batch = {}
 
     def _buffers(self, h, w):
         torch = self.torch
@@ -106,3 +107,28 @@ class ShardedRenderer:
             return None
         self.ctx.detile(gathered.data_ptr(), frame.data_ptr(), h, w, self.world)
         return frame
+
+    def render_batch(self, jobs):
+        """jobs: sequence of (h, w, prepared, spp).  All shards are rendered by ONE ray_b200_render_batch call (two frames
+        in flight: a frame's long-path tail is covered by the next frame's start), then gathered and de-tiled frame by
+        frame.  Returns the list of full frames on rank 0 (each valid until the next call with the same job slot), None
+        elsewhere.  Put the frame with the longest tail first."""
+        torch = self.torch
+        dev = torch.device("cuda", self.ctx.device)
+        bufs = []
+        for slot, (h, w, _, _) in enumerate(jobs):
+            key = (slot, h, w)
+            if key not in self._batch:
+                _, _, _, padded = tile_layout(h, w, self.world)
+                self._batch[key] = (torch.empty((padded, TILE_PIXELS), dtype=torch.int32, device=dev),
+                                    torch.empty((h, w), dtype=torch.int32, device=dev) if self.rank == 0 else None)
+            bufs.append(self._batch[key])
+        self.ctx.render_batch([dict(prepared=pr, h=h, w=w, spp=spp, shard_layout=True, out_dev=b[0].data_ptr())
+                               for (h, w, pr, spp), b in zip(jobs, bufs)])
+        frames = []
+        for (h, w, _, _), (tiles, frame) in zip(jobs, bufs):
+            gathered = gather_tiles(tiles, dst=0)
+            if self.rank == 0:
+                self.ctx.detile(gathered.data_ptr(), frame.data_ptr(), h, w, self.world)
+                frames.append(frame)
+        return frames if self.rank == 0 else None

@@ -163,6 +163,98 @@ def test_streamqueue_variants(R, oracle, golden, tuning):
     assert_same(gpu_frame(R, "random", 64, 96, "streamqueue", n=60000, seed=3, **tuning), w3, f"streamqueue {tuning} deep tree")
 
 
+@pytest.mark.parametrize("heavy_first", [0, 1])
+def test_heavy_first_claim_order_is_invisible(R, oracle, golden, heavy_first):
+    """The probe pass + sorted claim order only change WHEN a tile is rendered: reference PNGs, partial tiles at
+    spp > 1 (row-major and compact sharded layouts), a deep tree, pixel-bound K3 and the warp trace must all be unchanged."""
+    import torch
+    from raytracers_b200 import distributed as D
+    for name in ("rgbbox_500", "irreg_500"):
+        want, _ = golden[name]
+        assert_same(gpu_frame(R, name.split("_")[0], 500, 500, "warpqueue", heavy_first=heavy_first), want, f"heavy_first={heavy_first} {name}")
+    h, w, spp = 45, 83, 5
+    want, want_rgb, _ = oracle.Scene.rgbbox().prepare(h, w).render(h, w, spp=spp, want_rgb=True)
+    for extra in (dict(), dict(wq_spread=0), dict(wq_packet=8)):
+        with R.Context(kernel="warpqueue", heavy_first=heavy_first, **extra) as ctx:
+            ctx.trace_warps(True)
+            pr = ctx.prepare_scene(h, w, ctx.rgbbox())
+            pix, rgb = ctx.render_host(h, w, pr, spp=spp, want_rgb=True)
+            assert_same(pix, want, f"heavy_first={heavy_first} {extra}")
+            np.testing.assert_array_equal(rgb.view(np.uint32), want_rgb.view(np.uint32))
+            t = ctx.warp_trace()
+            assert t.size % 148 == 0 and (t >= 0).all() and t.max() < 1e6
+            world = 3
+            padded = D.tile_layout(h, w, world)[3]
+            for rank in range(world):
+                tiles = torch.empty((padded, 32), dtype=torch.int32, device="cuda")
+                ctx.set_shard(rank, world)
+                ctx.render_shard_into(tiles.data_ptr(), h, w, pr, spp=spp)
+                ctx.sync()
+                np.testing.assert_array_equal(tiles.cpu().numpy(), D.extract_rank_tiles(want, rank, world))
+    w3, _, _ = oracle.render_scene("random", 64, 96, n=60000, seed=3)
+    assert_same(gpu_frame(R, "random", 64, 96, "warpqueue", n=60000, seed=3, heavy_first=heavy_first), w3, "deep tree")
+    # one tile / one pixel frames: nothing to order
+    w4, _, _ = oracle.Scene.rgbbox().prepare(3, 5).render(3, 5, spp=2)
+    assert_same(gpu_frame(R, "rgbbox", 3, 5, "warpqueue", spp=2, heavy_first=heavy_first), w4, "single tile")
+
+
+@pytest.mark.parametrize("kernel", ["warpqueue", "persistent", "mega", "wavefront", "streamqueue"])
+def test_render_batch_two_frames_in_flight(R, oracle, kernel):
+    """ray_b200_render_batch: frames of different scenes / sizes / spp submitted as one stream-ordered operation (two in
+    flight) are bit-identical to the oracle, in the row-major and the compact shard layout, with and without float output."""
+    import torch
+    from raytracers_b200 import distributed as D
+    cases = [("irreg", 64, 96, 5), ("rgbbox", 45, 83, 1), ("rgbbox", 45, 83, 5), ("irreg", 30, 50, 2), ("rgbbox", 8, 8, 3)]
+    want = {c: getattr(oracle.Scene, c[0])().prepare(c[1], c[2]).render(c[1], c[2], spp=c[3], want_rgb=True) for c in cases}
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream), R.Context(kernel=kernel) as ctx:
+        ctx.set_stream(stream.cuda_stream)
+        scenes = {n: ctx.scene(n) for n in ("rgbbox", "irreg")}
+        prep = {c: ctx.prepare_scene(c[1], c[2], scenes[c[0]]) for c in cases}
+        for rep in range(3):  # the lanes' scratch (cursor, sample buffers) is reused across batches
+            pix = {c: torch.full((c[1], c[2]), -1, dtype=torch.int32, device="cuda") for c in cases}
+            rgb = {c: torch.zeros((c[1], c[2], 3), dtype=torch.float32, device="cuda") for c in cases[:3]}
+            ctx.render_batch([dict(prepared=prep[c], h=c[1], w=c[2], spp=c[3], out_dev=pix[c].data_ptr(),
+                                   out_rgb_dev=rgb[c].data_ptr() if c in rgb else None) for c in cases])
+            got = {c: pix[c].cpu().numpy() for c in cases}  # same stream: ordered after the whole batch
+            assert ctx.last_render_ms() > 0
+            for c in cases:
+                assert_same(got[c], want[c][0], f"batch {kernel} {c} rep {rep}")
+            for c in rgb:
+                np.testing.assert_array_equal(rgb[c].cpu().numpy().view(np.uint32), want[c][1].view(np.uint32))
+        world = 3
+        for rank in range(world):
+            ctx.set_shard(rank, world)
+            tiles = {c: torch.full((D.tile_layout(c[1], c[2], world)[3], 32), -1, dtype=torch.int32, device="cuda") for c in cases}
+            ctx.render_batch([dict(prepared=prep[c], h=c[1], w=c[2], spp=c[3], shard_layout=True, out_dev=tiles[c].data_ptr()) for c in cases])
+            for c in cases:
+                np.testing.assert_array_equal(tiles[c].cpu().numpy(), D.extract_rank_tiles(want[c][0], rank, world))
+        ctx.set_shard(0, 1)
+        ctx.render_batch([])
+        with pytest.raises(R.RayError):
+            ctx.render_batch([dict(prepared=prep[cases[0]], h=64, w=96, spp=1, out_dev=0)])
+        with pytest.raises(R.RayError):
+            ctx.render_batch([dict(prepared=prep[cases[0]], h=64, w=96, spp=1, shard_layout=True, out_dev=pix[cases[0]].data_ptr(),
+                                   out_rgb_dev=rgb[cases[0]].data_ptr())])
+
+
+def test_render_batch_headline_frames(R):
+    """1000x1000 64 spp rgbbox + irreg as one batch == the same frames rendered one by one."""
+    import torch
+    with R.Context() as ctx:
+        prep = {n: ctx.prepare_scene(1000, 1000, ctx.scene(n)) for n in ("irreg", "rgbbox")}
+        solo = {}
+        for n in prep:
+            solo[n] = torch.empty((1000, 1000), dtype=torch.int32, device="cuda")
+            ctx.render_into(solo[n].data_ptr(), 1000, 1000, prep[n], spp=64)
+        both = {n: torch.empty((1000, 1000), dtype=torch.int32, device="cuda") for n in prep}
+        for _ in range(2):
+            ctx.render_batch([dict(prepared=prep[n], h=1000, w=1000, spp=64, out_dev=both[n].data_ptr()) for n in prep])
+        ctx.sync()
+        for n in prep:
+            assert torch.equal(solo[n], both[n]), n
+
+
 def test_warpqueue_deep_tree_and_many_samples(R, oracle):
     """Deep tree (bigger per-warp stacks -> fewer warps fit) and a sample count larger than one ring round."""
     n, h, w = 150000, 64, 96
