@@ -539,6 +539,39 @@ int oracle_render(void *pv, int64_t h, int64_t w, int32_t spp, int32_t *out_pix,
   return 0;
 }
 
+// Per-pixel work of the reference traversal (sum over the samples): bvh_fold iterations and objs_hit calls.  Used to
+// study how evenly a tile -> GPU assignment spreads a frame (tools/shard_balance.py, tests); same loop as oracle_render.
+int oracle_render_cost(void *pv, int64_t h, int64_t w, int32_t spp, int32_t *out_iterations, int32_t *out_segments, int32_t threads) {
+  Prepared *p = (Prepared *)pv;
+  if (!p || h <= 0 || w <= 0 || spp <= 0 || !out_iterations) return 1;
+  std::vector<float> ox((size_t)spp), oy((size_t)spp);
+  for (int32_t s = 0; s < spp; s++) sample_offset(s, &ox[(size_t)s], &oy[(size_t)s]);
+  int nthreads = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+  if (nthreads < 1) nthreads = 1;
+  std::atomic<int64_t> next_row{0};
+  auto worker = [&]() {
+    for (;;) {
+      const int64_t j = next_row.fetch_add(1);
+      if (j >= h) break;
+      for (int64_t i = 0; i < w; i++) {
+        Counters local;
+        for (int32_t s = 0; s < spp; s++) {
+          float u = ((float)i + ox[(size_t)s]) / (float)w;
+          float v = ((float)(h - j) + oy[(size_t)s]) / (float)h;
+          if (spp == 1) { u = (float)i / (float)w; v = (float)(h - j) / (float)h; }
+          (void)ray_colour(p->objs, get_ray(p->cam, u, v), 50, &local);
+        }
+        out_iterations[j * w + i] = (int32_t)local.iterations;
+        if (out_segments) out_segments[j * w + i] = (int32_t)local.segments;
+      }
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 0; t < nthreads; t++) pool.emplace_back(worker);
+  for (auto &t : pool) t.join();
+  return 0;
+}
+
 int oracle_num_procs(void) { int n = (int)std::thread::hardware_concurrency(); return n > 0 ? n : 1; }
 
 // unit-test hooks -------------------------------------------------------------------------------

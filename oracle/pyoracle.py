@@ -54,6 +54,8 @@ def lib():
         L.oracle_prepared_dump.argtypes = [vp] * 8
         L.oracle_render.restype = C.c_int
         L.oracle_render.argtypes = [vp, i64, i64, i32, vp, vp, i32, i32, i32, C.POINTER(Counters)]
+        L.oracle_render_cost.restype = C.c_int
+        L.oracle_render_cost.argtypes = [vp, i64, i64, i32, vp, vp, i32]
         L.oracle_num_procs.restype = C.c_int
         L.oracle_morton_3d.restype = C.c_uint32
         L.oracle_morton_3d.argtypes = [f32, f32, f32]
@@ -160,6 +162,14 @@ class Prepared:
         if rc != 0:
             raise RuntimeError("oracle_render failed")
         return pix, rgb, cnt.as_dict()
+
+    def render_cost(self, h, w, spp=1, threads=0):
+        """Per-pixel work of the reference traversal: (bvh_fold iterations int32[h][w], objs_hit calls int32[h][w])."""
+        it = np.zeros((h, w), np.int32)
+        seg = np.zeros((h, w), np.int32)
+        if lib().oracle_render_cost(self._h, int(h), int(w), int(spp), _p(it), _p(seg), int(threads)) != 0:
+            raise RuntimeError("oracle_render_cost failed")
+        return it, seg
 
     def __del__(self):
         if getattr(self, "_h", None):

@@ -30,7 +30,7 @@ struct futhark_context_config {
   int32_t gpus = 1;  // > 1: this ONE process drives that many devices (RAY_GPUS; the drop-in multi-GPU mode of main.c)
   int32_t blocks_per_sm = 4, smem_budget = 48 * 1024, refill_min = 8, tail_from = 8;
   int32_t wq_warps = 24, wq_k = 1, wq_spread = 1, wq_packet = -1, wq_refill = 1, permute = 1, host_build = 0;
-  int32_t heavy_first = -1;  // pull long-path tiles to the front of the claim order: 0 off, 1/2/4 = probe pixels per tile, -1 = decide per frame
+  int32_t heavy_first = 0;   // pull long-path tiles to the front of the claim order: 0 off (default: the probe pass costs more than the tail it saves on one GPU, see profiles/), 1/2/4 = probe pixels per tile, -1 = on when spp > 1
   int32_t probe_segments = 8;
   std::string cache_file;
 };
