@@ -148,3 +148,22 @@ def test_spp1_is_the_reference_and_row_sampling(oracle):
     np.testing.assert_array_equal((q[..., 0] << 16) | (q[..., 1] << 8) | q[..., 2], full)
     one, _, _ = pr.render(64, 64, threads=1)
     np.testing.assert_array_equal(one, full)
+
+
+def test_per_pixel_cost_sums_to_the_counters_and_shards_evenly(oracle):
+    """oracle_render_cost (per-pixel bvh_fold iterations / objs_hit calls) is the same loop as oracle_render: its sums
+    equal the aggregate counters, also at spp > 1; and the tile -> rank rule of the multi-GPU path (8x4 tiles,
+    t % world) spreads that work evenly (the property behind 'no load balancing beyond interleaving')."""
+    from raytracers_b200 import distributed as D
+    for name, h, w, spp in (("rgbbox", 64, 96, 1), ("irreg", 50, 70, 3)):
+        pr = getattr(oracle.Scene, name)().prepare(h, w)
+        _, _, cnt = pr.render(h, w, spp=spp)
+        it, seg = pr.render_cost(h, w, spp=spp)
+        assert int(it.sum()) == cnt["iterations"] and int(seg.sum()) == cnt["segments"]
+        assert seg.min() >= spp
+    h = w = 400
+    it, _ = oracle.Scene.irreg().prepare(h, w).render_cost(h, w)
+    for world in (2, 4, 8):
+        per_rank = [int(D.extract_rank_tiles(it, r, world).sum()) for r in range(world)]
+        assert sum(per_rank) == int(it.sum())
+        assert max(per_rank) / (sum(per_rank) / world) < 1.05, (world, per_rank)
