@@ -11,9 +11,6 @@
 // See find_closest for how leaf tests are decoupled from the walk and how ties are broken.
 #include "render_params.h"
 #include <cub/cub.cuh>
-#ifndef RAYB200_PREFETCH
-#define RAYB200_PREFETCH 0
-#endif
 #include "device_math.cuh"
 
 #include <cstdio>
@@ -55,17 +52,6 @@ struct StagedScene {  // top of the tree (BFS prefix) + optionally all spheres i
     }
   }
   __device__ __forceinline__ float4 sphere(int i) const { return kSpheres ? s_geom[i] : __ldg(geom + i); }
-  // experiment (-DRAYB200_PREFETCH=1): pull a just-queued child's record towards L1 while the item waits in the queue
-  __device__ __forceinline__ void prefetch_node(int idx) const {
-#if RAYB200_PREFETCH
-    if (!kAllNodes && idx >= smem_nodes) asm volatile("prefetch.global.L1 [%0];" ::"l"(nodes + 4 * (size_t)idx));
-#endif
-  }
-  __device__ __forceinline__ void prefetch_sphere(int i) const {
-#if RAYB200_PREFETCH
-    if (!kSpheres) asm volatile("prefetch.global.L1 [%0];" ::"l"(geom + i));
-#endif
-  }
 };
 
 // ------------------------------------------------------------------ objs_hit, first half (ray.fut:76-82)
@@ -881,12 +867,6 @@ __global__ void __launch_bounds__(kWqMaxThreads, 1) render_warpqueue_kernel(cons
       if (pl_leaf) lstk[lb] = tag | (uint32_t)(~lptr);
       if (pr_leaf) lstk[lb + (pl_leaf ? 1 : 0)] = tag | (uint32_t)(~rptr);
       ltop += __popc(cl) + __popc(cr);
-#if RAYB200_PREFETCH
-      if (pl_node) sc.prefetch_node(lptr);
-      if (pr_node) sc.prefetch_node(rptr);
-      if (pl_leaf) sc.prefetch_sphere(~lptr);
-      if (pr_leaf) sc.prefetch_sphere(~rptr);
-#endif
     };
     using full_t = std::integral_constant<bool, true>;
     using part_t = std::integral_constant<bool, false>;
