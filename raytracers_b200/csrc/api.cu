@@ -752,7 +752,17 @@ int futhark_context_clear_caches(struct futhark_context *ctx) {
   std::lock_guard<std::mutex> g(ctx->mu);
   cudaSetDevice(ctx->cfg.device);  // helper contexts of the single-process multi-GPU mode switch devices
   cudaMemPool_t pool;
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // lane 1 always joins the context's stream before a call returns
+  // grow-only scratch: finished-sample buffers, claim-order tables, wavefront ray queues, page-locked upload buffers
+  for (auto &L : ctx->lanes) {
+    if (L.sample_buf) cudaFree(L.sample_buf);
+    if (L.tile_order_block) cudaFree(L.tile_order_block);
+    L.sample_buf = nullptr; L.sample_buf_bytes = 0;
+    L.tile_order_block = nullptr; L.tile_order_bytes = 0;
+  }
+  free_wavefront(ctx);
+  for (auto &b : ctx->pinned_cache) { cudaEventDestroy(b.last_use); cudaFreeHost(b.ptr); }
+  ctx->pinned_cache.clear();
   if (cudaDeviceGetDefaultMemPool(&pool, ctx->cfg.device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
   return 0;
 }

@@ -414,6 +414,20 @@ def test_array_and_misc_api(R):
     L.futhark_context_free(ctxh)
 
 
+def test_clear_caches_then_render_again(R, oracle):
+    """futhark_context_clear_caches drops the grow-only scratch (sample buffers, ray queues, upload buffers); the next
+    prepare_scene / render must simply grow it again."""
+    h, w, spp = 33, 47, 4
+    want, _, _ = oracle.Scene.rgbbox().prepare(h, w).render(h, w, spp=spp)
+    for kernel in ("warpqueue", "wavefront"):
+        with R.Context(kernel=kernel) as ctx:
+            for _ in range(2):
+                pr = ctx.prepare_scene(h, w, ctx.rgbbox())
+                assert_same(ctx.render_host(h, w, pr, spp=spp), want, f"{kernel} around clear_caches")
+                pr.free()
+                assert ctx.lib.futhark_context_clear_caches(ctx.handle) == 0
+
+
 def test_store_restore_and_reupload(R, oracle):
     h, w = 40, 56
     want, _, _ = oracle.render_scene("irreg", h, w)
