@@ -138,6 +138,8 @@ struct ray_b200_render_job {
   float *out_rgb_dev;   /* device float[h][w][3] or NULL (row-major layout only) */
 };
 int ray_b200_render_batch(struct futhark_context *ctx, const struct ray_b200_render_job *jobs, int32_t n);
+/* sizeof(struct ray_b200_render_job) as the library was compiled: lets a foreign-language binding check its layout. */
+int64_t ray_b200_render_job_size(void);
 /* gathered_dev: int32[world][tiles_padded][32] (rank-major, as produced by an NCCL gather);
  * writes the row-major image int32[h][w] to out_pix_dev. */
 int ray_b200_detile(struct futhark_context *ctx, const int32_t *gathered_dev, int32_t *out_pix_dev, int64_t h,

@@ -110,6 +110,7 @@ def load_library():
         "ray_b200_context_device": (C.c_int, [vp]),
         "ray_b200_context_last_render_ms": (C.c_int, [vp, C.POINTER(C.c_float)]),
         "ray_b200_render_batch": (C.c_int, [vp, C.POINTER(RenderJob), C.c_int32]),
+        "ray_b200_render_job_size": (C.c_int64, []),
         "ray_b200_context_trace_warps": (C.c_int, [vp, C.c_int32]),
         "ray_b200_context_warp_trace": (C.c_int, [vp, C.POINTER(C.c_float), C.c_int64, C.POINTER(C.c_int64)]),
         "ray_b200_context_launch_count": (i64, [vp]),

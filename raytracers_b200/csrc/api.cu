@@ -1298,6 +1298,8 @@ int ray_b200_render_batch(struct futhark_context *ctx, const struct ray_b200_ren
   return rc;
 }
 
+int64_t ray_b200_render_job_size(void) { return (int64_t)sizeof(struct ray_b200_render_job); }
+
 int ray_b200_detile(struct futhark_context *ctx, const int32_t *gathered_dev, int32_t *out_pix_dev, int64_t h, int64_t w, int32_t world) {
   if (bad_ctx(ctx)) return 1;
   std::lock_guard<std::mutex> g(ctx->mu);

@@ -43,6 +43,12 @@ def test_python_binding_covers_the_headers(R):
     assert bound <= declared, bound - declared
 
 
+def test_struct_layouts_match_the_library(R):
+    """ctypes mirrors of the C structs have the size the library was compiled with (no GPU needed)."""
+    lib = R.load_library()
+    assert ctypes.sizeof(R.RenderJob) == lib.ray_b200_render_job_size() == 48
+
+
 def _compile(src, out, extra=()):
     cmd = ["/usr/bin/gcc", "-O3", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", src, "-o", out,
            "-I" + os.path.join(ROOT, "include"), "-L" + os.path.join(ROOT, "raytracers_b200"), "-lray_b200",
