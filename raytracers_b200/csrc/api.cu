@@ -29,7 +29,7 @@ struct futhark_context_config {
   int32_t rank = 0, world = 1;
   int32_t gpus = 1;  // > 1: this ONE process drives that many devices (RAY_GPUS; the drop-in multi-GPU mode of main.c)
   int32_t blocks_per_sm = 4, smem_budget = 48 * 1024, refill_min = 8, tail_from = 8;
-  int32_t wq_warps = 24, wq_k = 1, wq_spread = 1, wq_packet = -1, wq_refill = 1, permute = 1, host_build = 0;
+  int32_t wq_warps = 24, wq_k = 1, wq_spread = 1, wq_packet = -1, wq_refill = 1, wq_ncap = 512, permute = 1, host_build = 0;
   int32_t heavy_first = 0;   // pull long-path tiles to the front of the claim order: 0 off (default: the probe pass costs more than the tail it saves on one GPU, see profiles/), 1/2/4 = probe pixels per tile, -1 = on when spp > 1
   int32_t probe_segments = 8;
   std::string cache_file;
@@ -145,7 +145,7 @@ int parse_kernel(const char *v, int dflt) {
   return atoi(v);
 }
 
-const char *kTuningNames[] = {"kernel", "spp", "blocks_per_sm", "smem_budget", "refill_min", "tail_from", "wq_warps", "wq_k", "wq_spread", "wq_packet", "wq_refill", "permute", "heavy_first", "probe_segments", "host_build", "rank", "world", "gpus"};
+const char *kTuningNames[] = {"kernel", "spp", "blocks_per_sm", "smem_budget", "refill_min", "tail_from", "wq_warps", "wq_k", "wq_spread", "wq_packet", "wq_refill", "wq_ncap", "permute", "heavy_first", "probe_segments", "host_build", "rank", "world", "gpus"};
 constexpr int kNumTuning = sizeof(kTuningNames) / sizeof(kTuningNames[0]);
 
 bool bad_ctx(futhark_context *ctx) { return ctx == nullptr || !ctx->ok; }
@@ -245,7 +245,7 @@ int fill_params(futhark_context *ctx, const futhark_opaque_prepared_scene *p, in
     int64_t per_warp = 0, wq_w = 0;
     for (int attempt = 0; attempt < 2; attempt++) {
       const bool pk = want_packet != 0;
-      per_warp = (int64_t)wq_warp_bytes(k, wq_node_capacity(k, p->max_depth), pk);
+      per_warp = (int64_t)wq_warp_bytes(k, wq_node_capacity(k, p->max_depth, ctx->cfg.wq_ncap), pk);
       wq_w = ctx->cfg.wq_warps < 1 ? 1 : (ctx->cfg.wq_warps > kWqMaxWarps ? kWqMaxWarps : ctx->cfg.wq_warps);
       while (wq_w > 1 && wq_w * per_warp + 8192 > (int64_t)ctx->max_smem_optin) wq_w--;
       if (want_packet >= 0) break;
@@ -320,6 +320,7 @@ int do_render(futhark_context *ctx, RenderParams &P, int lane_id = 0, bool timed
   lc.wq_k = ctx->cfg.wq_k == 1 ? 1 : 2;
   lc.wq_refill = ctx->cfg.wq_refill < 1 ? 1 : (ctx->cfg.wq_refill > 32 ? 32 : ctx->cfg.wq_refill);
   lc.wq_packet = ctx->plan_wq_packet;
+  lc.wq_ncap = ctx->cfg.wq_ncap;
   if (lc.kernel == RAY_B200_KERNEL_WAVEFRONT && ensure_wavefront(ctx, P.local_tiles * kTilePixels)) return 1;
   P.sample_buf = nullptr;
   if ((lc.kernel == RAY_B200_KERNEL_WARPQUEUE || lc.kernel == RAY_B200_KERNEL_STREAMQUEUE) && P.spp > 1 && P.spp <= 65535 && ctx->cfg.wq_spread) {
@@ -543,6 +544,7 @@ int futhark_context_config_set_tuning_param(struct futhark_context_config *cfg, 
   else if (!strcmp(name, "wq_spread")) cfg->wq_spread = (int32_t)v;
   else if (!strcmp(name, "wq_refill")) cfg->wq_refill = (int32_t)v;
   else if (!strcmp(name, "wq_packet")) cfg->wq_packet = (int32_t)v;  // (size_t)-1 = decide per scene
+  else if (!strcmp(name, "wq_ncap")) cfg->wq_ncap = (int32_t)v;
   else if (!strcmp(name, "permute")) cfg->permute = (int32_t)v;
   else if (!strcmp(name, "heavy_first")) cfg->heavy_first = (int32_t)v;  // (size_t)-1 = decide per frame
   else if (!strcmp(name, "probe_segments")) cfg->probe_segments = (int32_t)v;
@@ -575,6 +577,7 @@ struct futhark_context *futhark_context_new(struct futhark_context_config *cfg) 
   ctx->cfg.wq_spread = env_int("RAY_WQ_SPREAD", ctx->cfg.wq_spread);
   ctx->cfg.wq_packet = env_int("RAY_WQ_PACKET", ctx->cfg.wq_packet);
   ctx->cfg.wq_refill = env_int("RAY_WQ_REFILL", ctx->cfg.wq_refill);
+  ctx->cfg.wq_ncap = env_int("RAY_WQ_NCAP", ctx->cfg.wq_ncap);
   ctx->cfg.permute = env_int("RAY_PERMUTE", ctx->cfg.permute);
   ctx->cfg.heavy_first = env_int("RAY_HEAVY_FIRST", ctx->cfg.heavy_first);
   ctx->cfg.probe_segments = env_int("RAY_PROBE_SEGMENTS", ctx->cfg.probe_segments);

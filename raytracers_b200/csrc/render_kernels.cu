@@ -1440,7 +1440,7 @@ void launch_render(const RenderParams &p, const LaunchConfig &lc, const Wavefron
   if (lc.kernel == 4) {  // RAY_B200_KERNEL_WARPQUEUE: one CTA per SM, wq_warps warps, 32*wq_k rays in flight per warp
     const int k = lc.wq_k == 1 ? 1 : 2;
     const int wthreads = 32 * lc.wq_warps;
-    const int ncap = wq_node_capacity(k, p.max_depth);
+    const int ncap = wq_node_capacity(k, p.max_depth, lc.wq_ncap);
     const bool packet = lc.wq_packet > 0;
     const size_t wsmem = ((staging_bytes(p) + 127) & ~(size_t)127) + (size_t)lc.wq_warps * wq_warp_bytes(k, ncap, packet);
     long long ctas = lc.sm_count;

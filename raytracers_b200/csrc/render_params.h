@@ -74,6 +74,7 @@ struct LaunchConfig {
   int wq_k;            // warp-queue kernel: rays in flight per warp = 32 * wq_k (1 or 2)
   int wq_refill;       // warp-queue kernel, spread mode: hand out samples when at least this many slots are idle
   int wq_packet;       // warp-queue kernel: node steps with at least this many lanes are done packet-style (0 = never)
+  int wq_ncap;         // warp-queue kernel: cap on the node-queue capacity (0 = the proved bound, at most 1024)
 };
 
 void launch_render(const RenderParams &p, const LaunchConfig &lc, const WavefrontBuffers *wf, cudaStream_t stream,
@@ -114,6 +115,11 @@ __host__ __device__ inline int wq_node_capacity(int k, int max_depth) {
   // capped at 1024 entries instead of costing warps or staging space
   const int c = 32 * k + 64 * (max_depth + 1);
   return c < 256 ? 256 : (c > 1024 ? 1024 : c);
+}
+// ... optionally capped further (tuning parameter wq_ncap, 0 = no cap): trades queue space for staged BVH nodes
+__host__ __device__ inline int wq_node_capacity(int k, int max_depth, int cap) {
+  const int c = wq_node_capacity(k, max_depth);
+  return cap > 0 && cap < c ? (cap < 256 ? 256 : cap) : c;
 }
 __host__ __device__ inline size_t wq_warp_bytes(int k, int ncap, bool packet) {
   const size_t r = 32 * (size_t)k;

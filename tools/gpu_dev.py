@@ -55,6 +55,7 @@ def main():
     ap.add_argument("--permute", default="1")
     ap.add_argument("--wq_packet", default="0")
     ap.add_argument("--wq_refill", default="1")
+    ap.add_argument("--wq_ncap", default="0")
     a = ap.parse_args()
     rows = []
     for cfg in a.configs.split(","):
@@ -68,7 +69,7 @@ def main():
             elif kernel == "wavefront":
                 grid = itertools.product(a.blocks_per_sm.split(","), a.tail_from.split(","), a.smem_budget.split(","))
             elif kernel in ("warpqueue", "streamqueue"):
-                grid = itertools.product(a.wq_warps.split(","), a.wq_refill.split(","), a.wq_packet.split(","))
+                grid = itertools.product(a.wq_warps.split(","), a.wq_ncap.split(","), a.wq_packet.split(","))
             else:
                 grid = itertools.product(a.blocks_per_sm.split(","), a.refill_min.split(","), a.smem_budget.split(","))
             for bps, rf, sb in grid:
@@ -77,7 +78,7 @@ def main():
                 elif kernel == "wavefront":
                     tuning = dict(blocks_per_sm=int(bps), tail_from=int(rf), smem_budget=int(sb))
                 elif kernel in ("warpqueue", "streamqueue"):
-                    tuning = dict(wq_warps=int(bps), wq_refill=int(rf), wq_packet=int(sb))
+                    tuning = dict(wq_warps=int(bps), wq_ncap=int(rf), wq_packet=int(sb), wq_refill=int(a.wq_refill.split(",")[0]))
                 else:
                     tuning = dict(blocks_per_sm=int(bps), refill_min=int(rf), smem_budget=int(sb))
                 t0 = time.time()
