@@ -29,7 +29,7 @@ struct futhark_context_config {
   int32_t rank = 0, world = 1;
   int32_t gpus = 1;  // > 1: this ONE process drives that many devices (RAY_GPUS; the drop-in multi-GPU mode of main.c)
   int32_t blocks_per_sm = 4, smem_budget = 48 * 1024, refill_min = 8, tail_from = 8;
-  int32_t wq_warps = 24, wq_k = 1, wq_spread = 1, wq_packet = -1, wq_refill = 1, wq_ncap = 512, permute = 1, host_build = 0;
+  int32_t wq_warps = 0 /* 0 = per scene: 32, or 24 for trees far larger than the caches */, wq_k = 1, wq_spread = 1, wq_packet = -1, wq_refill = 1, wq_ncap = 512, permute = 1, host_build = 0;
   int32_t heavy_first = 0;   // pull long-path tiles to the front of the claim order: 0 off (default: the probe pass costs more than the tail it saves on one GPU, see profiles/), 1/2/4 = probe pixels per tile, -1 = on when spp > 1
   int32_t probe_segments = 8;
   std::string cache_file;
@@ -225,7 +225,7 @@ int fill_params(futhark_context *ctx, const futhark_opaque_prepared_scene *p, in
   if (resolve_kernel(ctx) == RAY_B200_KERNEL_STREAMQUEUE) {
     const int k = 1;
     const int64_t per_warp = (int64_t)sq_warp_bytes(k, wq_node_capacity(k, p->max_depth));
-    int64_t wq_w = ctx->cfg.wq_warps < 1 ? 1 : (ctx->cfg.wq_warps > kWqMaxWarps ? kWqMaxWarps : ctx->cfg.wq_warps);
+    int64_t wq_w = ctx->cfg.wq_warps < 1 ? 24 : (ctx->cfg.wq_warps > kWqMaxWarps ? kWqMaxWarps : ctx->cfg.wq_warps);
     while (wq_w > 1 && wq_w * per_warp + 8192 > (int64_t)ctx->max_smem_optin) wq_w--;
     budget = (int64_t)ctx->max_smem_optin - wq_w * per_warp - 512;
     if (budget < 256) { set_error(ctx, "render: stream-queue kernel does not fit shared memory (tree depth %d)", p->max_depth); return 1; }
@@ -233,7 +233,7 @@ int fill_params(futhark_context *ctx, const futhark_opaque_prepared_scene *p, in
     ctx->plan_wq_warps = (int32_t)wq_w;
   }
   if (resolve_kernel(ctx) == RAY_B200_KERNEL_WARPQUEUE) {
-    // one CTA per SM: as many warps as asked for (<= 24) while their queues leave >= 8 KB for staging;
+    // one CTA per SM: as many warps as asked for (<= 32) while their queues leave >= 8 KB for staging;
     // deep trees need bigger node stacks, so they get fewer warps
     const int k = ctx->cfg.wq_k == 1 ? 1 : 2;
     // Packet steps pay off when item-mode node fetches are expensive (part of the tree not staged in shared memory)
@@ -246,7 +246,10 @@ int fill_params(futhark_context *ctx, const futhark_opaque_prepared_scene *p, in
     for (int attempt = 0; attempt < 2; attempt++) {
       const bool pk = want_packet != 0;
       per_warp = (int64_t)wq_warp_bytes(k, wq_node_capacity(k, p->max_depth, ctx->cfg.wq_ncap), pk);
-      wq_w = ctx->cfg.wq_warps < 1 ? 1 : (ctx->cfg.wq_warps > kWqMaxWarps ? kWqMaxWarps : ctx->cfg.wq_warps);
+      // 32 warps hide latency best while the tree is cache-resident (rgbbox, irreg); the 1 M-sphere tree (64 MB of
+      // nodes) runs 8 % faster with 24 warps, i.e. more L1 per warp (profiles/r1_sweep_cta_size.json)
+      const int auto_warps = (int64_t)(p->n - 1) * 64 <= ((int64_t)8 << 20) ? 32 : 24;
+      wq_w = ctx->cfg.wq_warps < 1 ? auto_warps : (ctx->cfg.wq_warps > kWqMaxWarps ? kWqMaxWarps : ctx->cfg.wq_warps);
       while (wq_w > 1 && wq_w * per_warp + 8192 > (int64_t)ctx->max_smem_optin) wq_w--;
       if (want_packet >= 0) break;
       const int64_t b = (int64_t)ctx->max_smem_optin - wq_w * per_warp - 512 - 128;

@@ -100,8 +100,11 @@ void launch_detile(const int32_t *gathered, int32_t *out, int64_t H, int64_t W, 
 __host__ __device__ inline size_t staging_bytes(const RenderParams &p) {
   return 128 + (size_t)p.smem_nodes * 64 + (size_t)p.smem_spheres * 16;
 }
+// CTA size bound of the warp-queue kernels = their register budget: 1024 threads -> 64 registers (a few spills in the
+// cold paths), 768 -> 80.  Measured (profiles/r1_sweep_cta_size.json): 32 warps x 64 registers beat 24 x 80 by 6 % on
+// rgbbox, 7 % on irreg (64 spp), 10 % on irreg 4000^2 — the kernel is bound by issue slots and latency, not registers.
 #ifndef RAYB200_WQ_THREADS
-#define RAYB200_WQ_THREADS 768
+#define RAYB200_WQ_THREADS 1024
 #endif
 constexpr int kWqMaxThreads = RAYB200_WQ_THREADS;  // warp-queue kernel: CTA size bound (one CTA per SM) -> register budget
 constexpr int kWqMaxWarps = kWqMaxThreads / 32;

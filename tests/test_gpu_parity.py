@@ -94,7 +94,7 @@ def test_spp_extension_vs_oracle(R, oracle, name, spp, kernel):
 
 
 @pytest.mark.parametrize("tuning", [dict(wq_spread=1, wq_warps=16, wq_k=1), dict(wq_spread=1, wq_warps=3, wq_k=2),
-                                    dict(wq_spread=0, wq_warps=8, wq_k=2), dict(wq_spread=1, wq_warps=24, wq_k=1)])
+                                    dict(wq_spread=0, wq_warps=8, wq_k=2), dict(wq_spread=1, wq_warps=24, wq_k=1), dict(wq_warps=32), dict(wq_warps=32, wq_k=2)])
 def test_warpqueue_sample_spreading(R, oracle, tuning):
     """spp > 1 on the warp-queue kernel: samples of a pixel are traced by different lanes and summed in
     sample order afterwards — must be bit-identical to the sequential definition, also on partial tiles
