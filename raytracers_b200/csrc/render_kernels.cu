@@ -1420,9 +1420,11 @@ void launch_render(const RenderParams &p, const LaunchConfig &lc, const Wavefron
     const int ncap = wq_node_capacity(k, p.max_depth);
     const size_t wsmem = ((staging_bytes(p) + 127) & ~(size_t)127) + (size_t)lc.wq_warps * sq_warp_bytes(k, ncap);
     long long ctas = lc.sm_count;
-    const long long useful = (items + 32 * k * lc.wq_warps - 1) / (32 * k * lc.wq_warps);
-    if (ctas > useful) ctas = useful;
     const bool spread = p.sample_buf != nullptr;
+    // no more CTAs than there are rays to start at once: a slot takes one SAMPLE when samples are spread, one pixel otherwise
+    const long long rays = items * (spread ? (long long)p.spp : 1ll);
+    const long long useful = (rays + 32 * k * lc.wq_warps - 1) / (32 * k * lc.wq_warps);
+    if (ctas > useful) ctas = useful;
 #define RAYB200_SQ(KK, SP, A, S) render_streamqueue_kernel<KK, SP, A, S><<<(unsigned)ctas, wthreads, wsmem, stream>>>(p, ncap, lc.wq_refill)
 #define RAYB200_SQ2(KK, SP)                                                               \
   do {                                                                                    \
@@ -1444,7 +1446,11 @@ void launch_render(const RenderParams &p, const LaunchConfig &lc, const Wavefron
     const bool packet = lc.wq_packet > 0;
     const size_t wsmem = ((staging_bytes(p) + 127) & ~(size_t)127) + (size_t)lc.wq_warps * wq_warp_bytes(k, ncap, packet);
     long long ctas = lc.sm_count;
-    const long long useful = (items + 32 * k * lc.wq_warps - 1) / (32 * k * lc.wq_warps);
+    const bool spread = p.sample_buf != nullptr;
+    // no more CTAs than there are rays to start at once: a slot takes one SAMPLE when samples are spread, one pixel
+    // otherwise (capping by pixels alone left 26 SMs idle on a 125 K-pixel shard at 64 spp with 32 warps per CTA)
+    const long long rays = items * (spread ? (long long)p.spp : 1ll);
+    const long long useful = (rays + 32 * k * lc.wq_warps - 1) / (32 * k * lc.wq_warps);
     if (ctas > useful) ctas = useful;
 #define RAYB200_WQ(KK, SP, PK, A, S) \
   render_warpqueue_kernel<KK, SP, PK, A, S><<<(unsigned)ctas, wthreads, wsmem, stream>>>(p, ncap, lc.wq_packet, lc.wq_refill)
@@ -1459,7 +1465,6 @@ void launch_render(const RenderParams &p, const LaunchConfig &lc, const Wavefron
   do {                                                                                    \
     if (packet) RAYB200_WQ2(KK, SP, true); else RAYB200_WQ2(KK, SP, false);               \
   } while (0)
-    const bool spread = p.sample_buf != nullptr;
     if (k == 1) { if (spread) RAYB200_WQ3(1, true); else RAYB200_WQ3(1, false); }
     else { if (spread) RAYB200_WQ3(2, true); else RAYB200_WQ3(2, false); }
 #undef RAYB200_WQ3
