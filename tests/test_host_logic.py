@@ -81,3 +81,44 @@ def test_shard_layout_matches_the_library(R, h, w, world):
     img = np.arange(h * w, dtype=np.int32).reshape(h, w) + 1
     gathered = np.stack([D.extract_rank_tiles(img, r, world) for r in range(world)])
     np.testing.assert_array_equal(D.detile_reference(gathered, h, w, world), img)
+
+
+def _adversarial_scene(rng, n, mode):
+    s = np.zeros((n, 7), np.float32)
+    if mode == "grid":        # few distinct centres -> many duplicate Morton codes (tie-break 32 + clz(i ^ j))
+        s[:, :3] = rng.integers(0, 3, size=(n, 3)).astype(np.float32)
+    elif mode == "line":      # two degenerate axes: (max - min) = 0 -> 0/0 = NaN -> Morton coordinate 0
+        s[:, 0] = rng.random(n, dtype=np.float32) * 100
+    elif mode == "plane":
+        s[:, [0, 2]] = rng.random((n, 2), dtype=np.float32) * 50 - 25
+    elif mode == "huge":      # extreme magnitudes: clamp(x * 1024, 0, 1023) and float rounding in the normalisation
+        s[:, :3] = (rng.random((n, 3), dtype=np.float32) - 0.5) * np.float32(1e30)
+    else:
+        s[:, :3] = rng.standard_normal((n, 3)).astype(np.float32) * 10
+    s[:, 3:6] = rng.random((n, 3), dtype=np.float32)
+    s[:, 6] = rng.random(n, dtype=np.float32) * 2 + np.float32(0.01)
+    return s
+
+
+@pytest.mark.parametrize("mode", ["grid", "line", "plane", "huge", "cloud"])
+def test_lbvh_matches_oracle_on_adversarial_scenes(R, oracle, mode):
+    """Host builder == oracle, array for array and bit for bit, on inputs chosen to stress S14-S18: duplicate keys,
+    NaN Morton axes, clamping, stale refits at awkward n (powers of two +-1)."""
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(mode.encode()))
+    cam = np.float32([0, 0, 50, 0, 0, 0, 60])
+    for n in (2, 3, 4, 5, 7, 8, 9, 31, 32, 33, 100, 257, 1000):
+        s = _adversarial_scene(rng, n, mode)
+        got = R.host_lbvh(s)
+        want_pr = oracle.Scene.custom(s, cam).prepare(16, 16)
+        want = want_pr.dump()
+        for k in ("morton", "perm", "left", "right", "parent"):
+            np.testing.assert_array_equal(got[k], want[k], err_msg=f"{mode} n={n} {k}")
+        np.testing.assert_array_equal(bits(got["boxes"]), bits(want["boxes"]), err_msg=f"{mode} n={n} boxes")
+        assert got["refit_sweeps"] == want_pr.sweeps
+        # structural invariants of a Karras tree: every leaf and every inner node except the root has exactly one parent
+        refs = np.concatenate([got["left"], got["right"]])
+        leaves = np.sort(~refs[refs < 0])
+        inner = np.sort(refs[refs >= 0])
+        np.testing.assert_array_equal(leaves, np.arange(n))
+        np.testing.assert_array_equal(inner, np.arange(1, n - 1))
