@@ -564,3 +564,27 @@ def test_large_frame_properties(R):
     assert sha(a) == sha(b)
     small = gpu_frame(R, "irreg", 1000, 1000, "persistent")
     np.testing.assert_array_equal(a[0, ::4], small[0])  # row 0: v = 1, u = i/W identical for i = 4k
+
+
+# Kept LAST in the file on purpose: it has not run on a GPU yet (see the reason), so nothing may depend on what it leaves behind.
+@pytest.mark.xfail(strict=False, reason="added after the round-1 GPU budget was spent: first run happens at round end; the host builder passes the same set on the CPU (tests/test_host_logic.py)")
+@pytest.mark.parametrize("mode", ["grid", "line", "plane", "huge", "cloud"])
+def test_device_lbvh_on_adversarial_scenes(R, oracle, mode):
+    """The device builder against the oracle on the adversarial set of tests/test_host_logic.py (duplicate keys, NaN
+    Morton axes, clamping, n around powers of two), plus a render of each scene."""
+    import zlib
+    from test_host_logic import _adversarial_scene
+    rng = np.random.default_rng(zlib.crc32(mode.encode()))
+    cam = np.float32([0, 0, 50, 0, 0, 0, 60])
+    with R.Context() as ctx:
+        for n in (2, 3, 4, 5, 7, 8, 9, 31, 32, 33, 100, 257, 1000):
+            s = _adversarial_scene(rng, n, mode)
+            want_pr = oracle.Scene.custom(s, cam).prepare(16, 24)
+            want = want_pr.dump()
+            pr = ctx.prepare_scene(16, 24, ctx.scene_from_arrays(s, cam))
+            got = pr.dump()
+            for k in ("morton", "perm", "left", "right", "parent"):
+                np.testing.assert_array_equal(got[k], want[k], err_msg=f"{mode} n={n} {k}")
+            np.testing.assert_array_equal(got["boxes"].view(np.uint32), want["boxes"].view(np.uint32), err_msg=f"{mode} n={n} boxes")
+            assert_same(ctx.render_host(16, 24, pr), want_pr.render(16, 24)[0], f"{mode} n={n} frame")
+            pr.free()
