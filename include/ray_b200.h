@@ -102,9 +102,11 @@ int64_t ray_b200_prepared_device_bytes(struct futhark_context *ctx, const struct
 int ray_b200_prepared_reupload(struct futhark_context *ctx, struct futhark_opaque_prepared_scene *p);
 
 /* ---- render extensions -------------------------------------------------------------------------- */
-/* render with explicit spp; optional float framebuffer.  out_pix_dev: device int32[h][w] (or NULL);
+/* render with explicit spp; optional float framebuffer.  out_pix_dev: device int32[h][w] (REQUIRED);
  * out_rgb_dev: device float[h][w][3] (or NULL).  Asynchronous on the context's stream.
- * With a shard set (world > 1) only this rank's pixels are written. */
+ * With a shard set (world > 1) only this rank's pixels are written.  On a single-process multi-GPU context
+ * (RAY_GPUS > 1) this call, ray_b200_render_shard_into and ray_b200_render_batch return an error: only
+ * futhark_entry_render / ray_b200_entry_render_spp gather the helper devices' tiles. */
 int ray_b200_render_into(struct futhark_context *ctx, int32_t *out_pix_dev, float *out_rgb_dev, int64_t h,
                          int64_t w, int32_t spp, const struct futhark_opaque_prepared_scene *p);
 /* Same, host buffers: H2D of nothing (the scene is resident), D2H of the frame, synchronous.

@@ -47,8 +47,10 @@ struct futhark_context {
   unsigned long long *counters = nullptr;   // device [4]
   unsigned long long *warp_trace = nullptr; // device [1 + SMs * kWqMaxWarps] when tracing is on (ray_b200_context_trace_warps)
   int trace_warps = 0;                      // warps per CTA of the last traced launch
-  float *offsets = nullptr;                 // device sample-offset table
+  float *offsets = nullptr;                 // device sample-offset table of the frame being set up (an entry of offset_tables)
   int32_t offsets_spp = 0;
+  struct OffsetTable { int32_t spp; float *dev; };
+  std::vector<OffsetTable> offset_tables;   // per-spp cache (ensure_offsets)
   int64_t launches = 0;
   WavefrontBuffers wf;                      // ray queues of the wavefront kernel (grown on demand)
   struct PinnedBlock { unsigned char *ptr; size_t bytes; cudaEvent_t last_use; };
@@ -62,7 +64,9 @@ struct futhark_context {
   size_t peer_tiles_bytes = 0;
   cudaEvent_t peer_done = nullptr;      // helper context: its shard has been rendered
   int32_t *gathered = nullptr;          // rank 0: [gpus][tiles_padded][32] staging for the de-tiling kernel (grow-only)
-  size_t gathered_bytes = 0;                // warps per CTA the warp-queue kernel will use for the frame being set up
+  size_t gathered_bytes = 0;
+  cudaEvent_t ev_gathered = nullptr;    // rank 0: the peer copies of the last frame have read every helper's peer_tiles
+  bool gather_pending = false;
   // Per-render scratch.  Lane 0 runs on the context's stream; lane 1 (own stream, created on first use) lets
   // ray_b200_render_batch keep two frames in flight so that one frame's tail is covered by the next frame's start.
   struct Lane {
@@ -150,14 +154,33 @@ constexpr int kNumTuning = sizeof(kTuningNames) / sizeof(kTuningNames[0]);
 
 bool bad_ctx(futhark_context *ctx) { return ctx == nullptr || !ctx->ok; }
 
+// Device copy of the sample-offset table for `spp` (offset (0,0) at sample 0).  Tables are cached per spp
+// (render_batch mixes sample counts) and never freed while a frame may still read them.  A new table is copied from a
+// page-locked staging buffer on the context's stream and the stream is synchronised before it is handed out, so the
+// data has landed whichever lane's stream the reading kernel is launched on (a pageable cudaMemcpy on the legacy stream
+// only guarantees staging, and nothing would order a non-blocking stream after its DMA).
 int ensure_offsets(futhark_context *ctx, int32_t spp) {
-  if (ctx->offsets && ctx->offsets_spp == spp) return 0;
+  for (auto &e : ctx->offset_tables)
+    if (e.spp == spp) { ctx->offsets = e.dev; ctx->offsets_spp = spp; return 0; }
   std::vector<float> table;
   sample_offsets(spp, table);
-  if (ctx->offsets) CUDA_TRY(ctx, cudaFree(ctx->offsets));
-  ctx->offsets = nullptr;
-  CUDA_TRY(ctx, cudaMalloc(&ctx->offsets, table.size() * sizeof(float)));
-  CUDA_TRY(ctx, cudaMemcpy(ctx->offsets, table.data(), table.size() * sizeof(float), cudaMemcpyHostToDevice));
+  const size_t bytes = table.size() * sizeof(float);
+  float *stage = nullptr, *dev = nullptr;
+  CUDA_TRY(ctx, cudaMallocHost(&stage, bytes));
+  memcpy(stage, table.data(), bytes);
+  cudaError_t e = cudaMalloc(&dev, bytes);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dev, stage, bytes, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFreeHost(stage);
+  if (e != cudaSuccess) { if (dev) cudaFree(dev); set_error(ctx, "sample-offset table upload failed: %s", cudaGetErrorString(e)); return 1; }
+  if (ctx->offset_tables.size() >= 32) {  // evict the oldest; every lane is drained first, so no frame still reads it
+    for (auto &L : ctx->lanes) if (L.stream) cudaStreamSynchronize(L.stream);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->offset_tables.front().dev);
+    ctx->offset_tables.erase(ctx->offset_tables.begin());
+  }
+  ctx->offset_tables.push_back({spp, dev});
+  ctx->offsets = dev;
   ctx->offsets_spp = spp;
   return 0;
 }
@@ -328,15 +351,19 @@ int do_render(futhark_context *ctx, RenderParams &P, int lane_id = 0, bool timed
   P.sample_buf = nullptr;
   if ((lc.kernel == RAY_B200_KERNEL_WARPQUEUE || lc.kernel == RAY_B200_KERNEL_STREAMQUEUE) && P.spp > 1 && P.spp <= 65535 && ctx->cfg.wq_spread) {
     // samples of a pixel are spread over a warp's slots; finished colours wait here for the in-order sum
+    // (0.6 MB per sample on a B200 with 32 warps).  Above a memory budget, or when the allocation fails, the frame falls
+    // back to the pixel-bound variant of the same kernel (kSpread = false), which handles any sample count.
     const size_t need = (size_t)lc.sm_count * lc.wq_warps * kWqRing * (size_t)P.spp * sizeof(float4);
-    if (need > L.sample_buf_bytes) {
+    constexpr size_t kSpreadBudget = (size_t)1 << 30;
+    bool have = need <= L.sample_buf_bytes;
+    if (!have && need <= kSpreadBudget) {
       CUDA_TRY(ctx, cudaStreamSynchronize(L.stream));
       if (L.sample_buf) CUDA_TRY(ctx, cudaFree(L.sample_buf));
       L.sample_buf = nullptr; L.sample_buf_bytes = 0;
-      CUDA_TRY(ctx, cudaMalloc(&L.sample_buf, need));
-      L.sample_buf_bytes = need;
+      if (cudaMalloc(&L.sample_buf, need) == cudaSuccess) { L.sample_buf_bytes = need; have = true; }
+      else { L.sample_buf = nullptr; cudaGetLastError(); }
     }
-    P.sample_buf = L.sample_buf;
+    P.sample_buf = have ? L.sample_buf : nullptr;
   }
   // heavy-first claim order (warp-queue kernel): worth its probe pass when a frame is long enough to have a tail to lose
   // — more than one sample per pixel — and pointless when every tile is claimed in the first wave anyway
@@ -691,6 +718,7 @@ void futhark_context_free(struct futhark_context *ctx) {
   if (ctx->peer_tiles) { cudaSetDevice(ctx->cfg.device); cudaFree(ctx->peer_tiles); }
   if (ctx->peer_done) cudaEventDestroy(ctx->peer_done);
   if (ctx->gathered) { cudaSetDevice(ctx->cfg.device); cudaFree(ctx->gathered); }
+  if (ctx->ev_gathered) cudaEventDestroy(ctx->ev_gathered);
   if (ctx->ok) {
     cudaSetDevice(ctx->cfg.device);
     cudaStreamSynchronize(ctx->stream);
@@ -705,7 +733,7 @@ void futhark_context_free(struct futhark_context *ctx) {
   if (ctx->lanes[1].stream) cudaStreamDestroy(ctx->lanes[1].stream);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
-  if (ctx->offsets) cudaFree(ctx->offsets);
+  for (auto &e : ctx->offset_tables) cudaFree(e.dev);
   if (ctx->counters) cudaFree(ctx->counters);
   if (ctx->warp_trace) cudaFree(ctx->warp_trace);
   if (ctx->d_build_result) cudaFree(ctx->d_build_result);
@@ -963,6 +991,7 @@ int ray_b200_entry_render_spp(struct futhark_context *ctx, struct futhark_i32_2d
     const int64_t padded = ray_b200_shard_tiles_padded(h, w, world);
     const size_t shard_bytes = (size_t)padded * kTilePixels * sizeof(int32_t);
     auto fail = [&](const char *what) { set_error(ctx, "render (multi-GPU): %s", what); cudaFreeAsync(img->dev, ctx->stream); delete img; return 1; };
+    if (!p) return fail("invalid prepared scene");
     if (p->peer_prepared.size() != ctx->peers.size()) return fail("prepared scene was not prepared by this context");
     if (ctx->gathered_bytes < shard_bytes * world) {
       cudaStreamSynchronize(ctx->stream);
@@ -981,6 +1010,9 @@ int ray_b200_entry_render_spp(struct futhark_context *ctx, struct futhark_i32_2d
         if (cudaMalloc(&peer->peer_tiles, shard_bytes) != cudaSuccess) { cudaSetDevice(ctx->cfg.device); return fail("out of device memory on a helper device"); }
         peer->peer_tiles_bytes = shard_bytes;
       }
+      // the previous frame's peer copy out of peer_tiles (on device 0's stream) must have finished before this helper
+      // renders into it again: entries are asynchronous, a caller may issue two renders without a sync in between
+      if (ctx->gather_pending) cudaStreamWaitEvent(peer->stream, ctx->ev_gathered, 0);
       if (ray_b200_render_shard_into(peer, peer->peer_tiles, h, w, spp, p->peer_prepared[(size_t)r - 1])) {
         char *pe = futhark_context_get_error(peer);
         cudaSetDevice(ctx->cfg.device);
@@ -1002,6 +1034,9 @@ int ray_b200_entry_render_spp(struct futhark_context *ctx, struct futhark_i32_2d
       cudaStreamWaitEvent(ctx->stream, peer->peer_done, 0);
       cudaMemcpyPeerAsync(ctx->gathered + (size_t)r * padded * kTilePixels, ctx->cfg.device, peer->peer_tiles, peer->cfg.device, shard_bytes, ctx->stream);
     }
+    if (!ctx->ev_gathered) cudaEventCreateWithFlags(&ctx->ev_gathered, cudaEventDisableTiming);
+    cudaEventRecord(ctx->ev_gathered, ctx->stream);  // every helper's tile buffer has been read
+    ctx->gather_pending = true;
     launch_detile(ctx->gathered, img->dev, h, w, world, padded, ctx->stream, &ctx->launches);
     if (cudaGetLastError() != cudaSuccess) return fail("de-tiling launch failed");
     *out0 = img;
@@ -1190,6 +1225,7 @@ int ray_b200_render_into(struct futhark_context *ctx, int32_t *out_pix_dev, floa
   if (bad_ctx(ctx)) return 1;
   std::lock_guard<std::mutex> g(ctx->mu);
   if (!out_pix_dev) { set_error(ctx, "render_into: out_pix_dev is required"); return 1; }
+  if (!ctx->peers.empty()) { set_error(ctx, "render_into: not available on a single-process multi-GPU context (RAY_GPUS > 1): only futhark_entry_render / ray_b200_entry_render_spp gather the helper devices' tiles"); return 1; }
   CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
   RenderParams P;
   if (fill_params(ctx, p, h, w, spp, ctx->cfg.rank, ctx->cfg.world, out_pix_dev, out_rgb_dev, false, P)) return 1;
@@ -1233,6 +1269,7 @@ int ray_b200_render_shard_into(struct futhark_context *ctx, int32_t *out_tiles_d
   if (bad_ctx(ctx)) return 1;
   std::lock_guard<std::mutex> g(ctx->mu);
   if (!out_tiles_dev) { set_error(ctx, "render_shard_into: null output"); return 1; }
+  if (!ctx->peers.empty()) { set_error(ctx, "render_shard_into: not available on a single-process multi-GPU context (RAY_GPUS > 1)"); return 1; }
   CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
   RenderParams P;
   if (fill_params(ctx, p, h, w, spp, ctx->cfg.rank, ctx->cfg.world, out_tiles_dev, nullptr, true, P)) return 1;
@@ -1252,6 +1289,7 @@ int ray_b200_render_batch(struct futhark_context *ctx, const struct ray_b200_ren
   std::lock_guard<std::mutex> g(ctx->mu);
   if (n < 0 || (n > 0 && !jobs)) { set_error(ctx, "render_batch: bad arguments"); return 1; }
   if (n == 0) return 0;
+  if (!ctx->peers.empty()) { set_error(ctx, "render_batch: not available on a single-process multi-GPU context (RAY_GPUS > 1)"); return 1; }
   CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
   for (int32_t i = 0; i < n; i++) {
     if (!jobs[i].out_dev) { set_error(ctx, "render_batch: job %d has no output buffer", i); return 1; }

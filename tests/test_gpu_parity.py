@@ -566,8 +566,6 @@ def test_large_frame_properties(R):
     np.testing.assert_array_equal(a[0, ::4], small[0])  # row 0: v = 1, u = i/W identical for i = 4k
 
 
-# Kept LAST in the file on purpose: it has not run on a GPU yet (see the reason), so nothing may depend on what it leaves behind.
-@pytest.mark.xfail(strict=False, reason="added after the round-1 GPU budget was spent: first run happens at round end; the host builder passes the same set on the CPU (tests/test_host_logic.py)")
 @pytest.mark.parametrize("mode", ["grid", "line", "plane", "huge", "cloud"])
 def test_device_lbvh_on_adversarial_scenes(R, oracle, mode):
     """The device builder against the oracle on the adversarial set of tests/test_host_logic.py (duplicate keys, NaN
