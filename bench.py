@@ -262,7 +262,10 @@ def run_ours(args):
     alg_bytes = {n: 32 * work[n]["box_tests"] + 16 * work[n]["leaf_tests"] + 4 * H * W for n in SCENES}
 
     frames = {n: torch.empty((H, W), dtype=torch.int32, device="cuda") for n in SCENES}
+    # N > 1: "peer" = every rank's kernel writes its pixels straight into rank 0's frame over NVLink (the gather fused into
+    # the render kernel, D.PeerFrameRenderer); "nccl" = compact tile buffers + one NCCL gather + de-tiling kernel per frame
     sharded = D.ShardedRenderer(ctx, rank, world) if world > 1 else None
+    peer = D.PeerFrameRenderer(ctx, rank, world, H, W, slots=4) if world > 1 and args.gather == "peer" else None
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
     # One step = every frame of the workload, submitted as ONE batch (ray_b200_render_batch: two frames in flight, so
@@ -278,6 +281,10 @@ def run_ours(args):
                     sharded.render(H, W, prepared[name], spp=SPP)
         elif sharded is None:
             ctx.render_batch([dict(prepared=prepared[n], h=H, w=W, spp=SPP, out_dev=frames[n].data_ptr()) for n in order])
+        elif peer is not None:
+            peer.render([(prepared[n], SPP) for n in order])
+            if rank == 0:   # the step ends when every rank's pixels of its frames have landed in rank 0's HBM
+                stream.wait_event(peer.landed)
         else:
             sharded.render_batch([(H, W, prepared[n], SPP) for n in order])
 
@@ -388,16 +395,40 @@ def run_ours(args):
         e2e = {"value": round(seg_per_step * args.steps / e2e_s / 1e6, 1), "unit": "Mrays/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": round(1e3 * e2e_s / args.steps, 3)}
     else:
-        # N > 1: the gathered frame's D2H on rank 0 inside the timed region
-        host = torch.empty((H, W), dtype=torch.int32, pin_memory=True) if rank == 0 else None
+        # N > 1, per step: H2D of every scene's sphere records + device LBVH build on every rank, all frames of the step as
+        # one batch, and every frame's D2H into page-locked memory on rank 0 - all inside the timed region.
+        # peer: the frames land in rank 0's ring over NVLink and are copied out on its copy stream while the next
+        # frames render (nothing blocks the host but the re-upload's own read-back);  nccl: gather + de-tile per frame,
+        # then a D2H on a second stream ordered by events.
+        if peer is not None and peer.flag_timeouts_safe():
+            raise SystemExit("bench.py: a peer-frame flag wait timed out")
+        host = [torch.empty((H, W), dtype=torch.int32, pin_memory=True) for _ in SCENES] if (rank == 0 and peer is None) else None
+        copy_stream = torch.cuda.Stream() if (rank == 0 and peer is None) else None
+        copied = [torch.cuda.Event() for _ in SCENES] if copy_stream is not None else None
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
+        for k in range(args.steps):
             for name in SCENES:
                 prepared[name].reupload()
-                fr = sharded.render(H, W, prepared[name], spp=SPP)
+            if peer is not None:
+                peer.render([(prepared[n], SPP) for n in order])
+            else:
+                if copied is not None and k > 0:
+                    for ev_c in copied:          # the frame buffers are reused: last step's copies must have read them
+                        stream.wait_event(ev_c)
+                frs = sharded.render_batch([(H, W, prepared[n], SPP) for n in order])
                 if rank == 0:
-                    host.copy_(fr, non_blocking=False)
+                    ready_ev = torch.cuda.Event()
+                    ready_ev.record(stream)
+                    copy_stream.wait_event(ready_ev)
+                    with torch.cuda.stream(copy_stream):
+                        for i, fr in enumerate(frs):
+                            host[i].copy_(fr, non_blocking=True)
+                            copied[i].record(copy_stream)
+        if peer is not None:
+            peer.wait()
+        elif copy_stream is not None:
+            copy_stream.synchronize()
         barrier()
         e2e_s = time.perf_counter() - t0
         tt = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
@@ -503,7 +534,8 @@ def run_ours(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "kernel": args.kernel, "spp": SPP, "segments_per_step": seg_per_step,
                        "l2": "flushed between timed steps (256 MiB memset outside the event pairs); scene is <1 MB",
-                       "parallelism": f"tile-sharded x{world}, one NCCL gather per frame" if world > 1 else "single GPU",
+                       "parallelism": (f"tile-sharded x{world}, " + ("pixels written straight into rank 0's frame over NVLink peer memory (gather fused into the render kernel)"
+                                                                      if args.gather == "peer" else "one NCCL gather per frame")) if world > 1 else "single GPU",
                        "submission": "frame by frame" if args.no_batch else "one ray_b200_render_batch per step (two frames in flight)",
                        "ray": "one ray segment = one objs_hit call (ray.fut:76-86)"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_issue": issue_all,
@@ -512,6 +544,9 @@ def run_ours(args):
             "published_reference_1spp_ms": PUBLISHED_1SPP_MS,
         }
         print(json.dumps(line), flush=True)
+    if peer is not None:
+        dist.barrier()
+        peer.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -544,6 +579,8 @@ def main():
     ap.add_argument("--no-extra", action="store_true",
                     help="skip the once-per-run measurement (outside the timed steps) of BASELINE configs[3] and [4]: irreg 4000x4000 at 1 / 256 spp and the 1M-sphere scene")
     ap.add_argument("--extra", action="store_true", help="(default now; kept for compatibility)")
+    ap.add_argument("--gather", default=os.environ.get("RAY_GATHER", "peer"), choices=["peer", "nccl"],
+                    help="N > 1: peer = ranks write their pixels straight into rank 0's frame over NVLink (default); nccl = tile buffers + ncclGather + de-tile")
     ap.add_argument("--workload", default="headline", choices=sorted(WORKLOADS),
                     help="headline = BASELINE configs[1]+[2] (the default the driver measures); irreg4000 = configs[3]")
     args = ap.parse_args()

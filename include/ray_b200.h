@@ -33,12 +33,14 @@ extern "C" {
 
 /* Render kernels (tuning param "kernel" / env RAY_KERNEL). */
 enum ray_b200_kernel {
-  RAY_B200_KERNEL_AUTO = 0,       /* the fastest measured variant: currently WARPQUEUE */
+  RAY_B200_KERNEL_AUTO = 0,       /* the fastest measured variant (see resolve_kernel in api.cu) */
   RAY_B200_KERNEL_MEGA = 1,       /* one thread per pixel, whole ray_colour loop (parity anchor) */
   RAY_B200_KERNEL_PERSISTENT = 2, /* persistent CTAs, TMA-staged BVH, per-lane dynamic path refill */
   RAY_B200_KERNEL_WAVEFRONT = 3,  /* per-bounce persistent kernel + global ray queues + warp-vote compaction */
   RAY_B200_KERNEL_WARPQUEUE = 4,  /* persistent; lanes bound to (ray,node) items on warp-private smem queues */
-  RAY_B200_KERNEL_STREAMQUEUE = 5 /* the same without rounds: per-ray item counters, finished rays refilled continuously */
+  RAY_B200_KERNEL_STREAMQUEUE = 5,/* the same without rounds: per-ray item counters, finished rays refilled continuously */
+  RAY_B200_KERNEL_LANEWALK = 6    /* persistent; a lane owns a ray's whole traversal (private smem stack), paths live in
+                                     warp-shared slots, finished segments are shaded in dense batches, no rounds */
 };
 
 /* ---- context extensions ---------------------------------------------------------------------- */
@@ -136,8 +138,16 @@ struct ray_b200_render_job {
   int32_t spp;          /* 0 = the context's default */
   int32_t shard_layout; /* 0: out_dev = int32[h][w], row-major (ray_b200_render_into);
                            1: out_dev = this rank's compact tiles int32[tiles_padded][32] (ray_b200_render_shard_into) */
-  int32_t *out_dev;     /* device */
+  int32_t *out_dev;     /* device (may be a PEER device's memory mapped with ray_b200_ipc_open: row-major layout + a
+                           shard set = every rank writes its own pixels straight into rank 0's frame over NVLink) */
   float *out_rgb_dev;   /* device float[h][w][3] or NULL (row-major layout only) */
+  /* peer-frame protocol (all optional, NULL = off), see "peer-memory frames" below:
+   * before the frame's kernel starts, its stream waits until *wait_flag >= wait_value (back-pressure from the consumer);
+   * when the last warp of the frame's kernel has written its pixels, *done_flag is incremented by 1 (system scope). */
+  uint32_t *wait_flag;
+  uint32_t wait_value;
+  uint32_t reserved0;
+  uint32_t *done_flag;
 };
 int ray_b200_render_batch(struct futhark_context *ctx, const struct ray_b200_render_job *jobs, int32_t n);
 /* sizeof(struct ray_b200_render_job) as the library was compiled: lets a foreign-language binding check its layout. */
@@ -146,6 +156,29 @@ int64_t ray_b200_render_job_size(void);
  * writes the row-major image int32[h][w] to out_pix_dev. */
 int ray_b200_detile(struct futhark_context *ctx, const int32_t *gathered_dev, int32_t *out_pix_dev, int64_t h,
                     int64_t w, int32_t world);
+
+/* ---- peer-memory frames: the gather fused into the render kernel ----------------------------------------
+ * One process per GPU.  Rank 0 allocates a ring of frames with ray_b200_ipc_alloc and hands the 64-byte handle to the
+ * other ranks (any transport: torch.distributed object broadcast in raytracers_b200/distributed.py); they map it with
+ * ray_b200_ipc_open and pass the mapped address as `out_dev` of a row-major render with their shard set.  The render
+ * kernel's pixel stores then ARE the collective: they travel over NVLink into rank 0's frame, no tile buffer, no
+ * ncclGather, no de-tiling kernel.  Completion and back-pressure are two 32-bit flags per frame slot in the same
+ * allocation (done_flag / wait_flag of ray_b200_render_job); the consumer side enqueues ray_b200_flag_wait on its copy
+ * stream, copies the frame out and publishes the slot again with ray_b200_flag_set. */
+#define RAY_B200_IPC_HANDLE_BYTES 64
+int ray_b200_ipc_alloc(struct futhark_context *ctx, int64_t bytes, void **dev_ptr, unsigned char *handle64);
+int ray_b200_ipc_free(struct futhark_context *ctx, void *dev_ptr);
+int ray_b200_ipc_open(struct futhark_context *ctx, const unsigned char *handle64, void **dev_ptr);
+int ray_b200_ipc_close(struct futhark_context *ctx, void *dev_ptr);
+/* Enqueue on `stream` (a cudaStream_t; NULL = the context's stream): spin until *flag >= value (system-scope acquire;
+ * gives up after timeout_ms and records an error that the next ray_b200_flag_status call returns). */
+int ray_b200_flag_wait(struct futhark_context *ctx, void *stream, uint32_t *flag_dev, uint32_t value, int32_t timeout_ms);
+/* Enqueue on `stream`: *flag = value (system-scope release). */
+int ray_b200_flag_set(struct futhark_context *ctx, void *stream, uint32_t *flag_dev, uint32_t value);
+/* Number of flag waits that timed out since the context was created (0 = healthy). */
+int ray_b200_flag_status(struct futhark_context *ctx, int64_t *timeouts);
+/* Enqueue on `stream`: device -> host copy (host_dst should be page-locked for the copy to be asynchronous). */
+int ray_b200_copy_to_host_async(struct futhark_context *ctx, void *stream, void *host_dst, const void *dev_src, int64_t bytes);
 
 /* ---- work counters (roofline numerators) ---------------------------------------------------------- */
 struct ray_b200_counters { uint64_t segments, node_steps, box_tests, leaf_tests; };

@@ -24,15 +24,20 @@ __all__ = ["Context", "RayError", "lib_path", "load_library", "KERNELS", "declar
            "host_camera", "host_lbvh", "host_sample_offsets"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-KERNELS = {"auto": 0, "mega": 1, "persistent": 2, "wavefront": 3, "warpqueue": 4, "streamqueue": 5}
+KERNELS = {"auto": 0, "mega": 1, "persistent": 2, "wavefront": 3, "warpqueue": 4, "streamqueue": 5, "lanewalk": 6}
+# The measured-slower alternative kernels are not part of the product library: they live in libray_b200_all.so (the
+# same objects + render_alt_kernels.cu built with RAYB200_ALL_KERNELS), which Context() loads when one of them is named.
+ALT_KERNELS = {2, 3, 5}
 
 
 class RayError(RuntimeError):
     pass
 
 
-def lib_path():
+def lib_path(variant=""):
     # RAY_B200_LIB: load another build of the same library (development A/B runs only)
+    if variant == "all":
+        return os.path.join(_HERE, "libray_b200_all.so")
     return os.environ.get("RAY_B200_LIB") or os.path.join(_HERE, "libray_b200.so")
 
 
@@ -53,18 +58,19 @@ class WorkCounters(C.Structure):
 class RenderJob(C.Structure):
     """struct ray_b200_render_job (include/ray_b200.h)."""
     _fields_ = [("prepared", C.c_void_p), ("h", C.c_int64), ("w", C.c_int64), ("spp", C.c_int32), ("shard_layout", C.c_int32),
-                ("out_dev", C.c_void_p), ("out_rgb_dev", C.c_void_p)]
+                ("out_dev", C.c_void_p), ("out_rgb_dev", C.c_void_p), ("wait_flag", C.c_void_p), ("wait_value", C.c_uint32),
+                ("reserved0", C.c_uint32), ("done_flag", C.c_void_p)]
 
 
-_lib = None
+_libs = {}
 
 
-def load_library():
-    """Loads libray_b200.so (built by `make -C raytracers_b200/csrc` / __graft_entry__.build())."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    path = lib_path()
+def load_library(variant=""):
+    """Loads libray_b200.so (built by `make -C raytracers_b200/csrc` / __graft_entry__.build()); variant "all" =
+    libray_b200_all.so, the build that also carries the alternative kernels K1 / K2 / K4."""
+    if variant in _libs:
+        return _libs[variant]
+    path = lib_path(variant)
     if not os.path.exists(path):
         raise RayError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                        "(there is no fallback implementation)")
@@ -132,6 +138,14 @@ def load_library():
         "ray_b200_render_shard_into": (C.c_int, [vp, vp, i64, i64, i32, vp]),
         "ray_b200_detile": (C.c_int, [vp, vp, vp, i64, i64, i32]),
         "ray_b200_count_work": (C.c_int, [vp, i64, i64, i32, vp, C.POINTER(WorkCounters)]),
+        "ray_b200_ipc_alloc": (C.c_int, [vp, i64, pp, vp]),
+        "ray_b200_ipc_free": (C.c_int, [vp, vp]),
+        "ray_b200_ipc_open": (C.c_int, [vp, vp, pp]),
+        "ray_b200_ipc_close": (C.c_int, [vp, vp]),
+        "ray_b200_flag_wait": (C.c_int, [vp, vp, vp, C.c_uint32, i32]),
+        "ray_b200_flag_set": (C.c_int, [vp, vp, vp, C.c_uint32]),
+        "ray_b200_flag_status": (C.c_int, [vp, C.POINTER(i64)]),
+        "ray_b200_copy_to_host_async": (C.c_int, [vp, vp, vp, vp, i64]),
         "ray_b200_host_scene": (C.c_int, [C.c_char_p, i64, u64, vp, i64, vp, C.POINTER(i64)]),
         "ray_b200_host_camera": (C.c_int, [vp, i64, i64, vp]),
         "ray_b200_host_lbvh": (C.c_int, [vp, i64, vp, vp, vp, vp, vp, vp, vp]),
@@ -143,7 +157,7 @@ def load_library():
         fn.restype = res
         fn.argtypes = args
     L._declared = tuple(sig)
-    _lib = L
+    _libs[variant] = L
     return L
 
 
@@ -333,7 +347,8 @@ class Context:
     """futhark_context + futhark_context_config (main.c:59-64)."""
 
     def __init__(self, device=None, kernel=None, spp=None, rank=None, world=None, **tuning):
-        self.lib = load_library()
+        kid = KERNELS[kernel] if isinstance(kernel, str) else kernel
+        self.lib = load_library("all" if kid in ALT_KERNELS else "")
         self.handle = None
         cfg = self.lib.futhark_context_config_new()
         if not cfg:
@@ -508,7 +523,48 @@ class Context:
             a.shard_layout = 1 if j.get("shard_layout") else 0
             a.out_dev = int(j["out_dev"])
             a.out_rgb_dev = int(j["out_rgb_dev"]) if j.get("out_rgb_dev") is not None else None
+            a.wait_flag = int(j["wait_flag"]) if j.get("wait_flag") else None   # peer-frame protocol (ray_b200.h)
+            a.wait_value = int(j.get("wait_value") or 0)
+            a.done_flag = int(j["done_flag"]) if j.get("done_flag") else None
         self._check(self.lib.ray_b200_render_batch(self.handle, arr, len(jobs)))
+
+    # -- peer-memory frames (include/ray_b200.h): raw device addresses as ints ---------------------------------
+    def ipc_alloc(self, nbytes):
+        """cudaMalloc'ed, zeroed device memory + its 64-byte CUDA IPC handle: (address, handle bytes)."""
+        ptr = C.c_void_p(None)
+        handle = (C.c_ubyte * 64)()
+        self._check(self.lib.ray_b200_ipc_alloc(self.handle, int(nbytes), C.byref(ptr), handle))
+        return int(ptr.value), bytes(handle)
+
+    def ipc_free(self, ptr):
+        self._check(self.lib.ray_b200_ipc_free(self.handle, C.c_void_p(int(ptr))))
+
+    def ipc_open(self, handle):
+        """Maps another process's ipc_alloc allocation (a peer GPU's memory over NVLink); returns the local address."""
+        ptr = C.c_void_p(None)
+        buf = (C.c_ubyte * 64).from_buffer_copy(bytes(handle))
+        self._check(self.lib.ray_b200_ipc_open(self.handle, buf, C.byref(ptr)))
+        return int(ptr.value)
+
+    def ipc_close(self, ptr):
+        self._check(self.lib.ray_b200_ipc_close(self.handle, C.c_void_p(int(ptr))))
+
+    def flag_wait(self, flag_ptr, value, stream=None, timeout_ms=5000):
+        self._check(self.lib.ray_b200_flag_wait(self.handle, C.c_void_p(int(stream) if stream else None), C.c_void_p(int(flag_ptr)),
+                                                int(value) & 0xffffffff, int(timeout_ms)))
+
+    def flag_set(self, flag_ptr, value, stream=None):
+        self._check(self.lib.ray_b200_flag_set(self.handle, C.c_void_p(int(stream) if stream else None), C.c_void_p(int(flag_ptr)),
+                                               int(value) & 0xffffffff))
+
+    def flag_timeouts(self):
+        n = C.c_int64(0)
+        self._check(self.lib.ray_b200_flag_status(self.handle, C.byref(n)))
+        return int(n.value)
+
+    def copy_to_host_async(self, host_ptr, dev_ptr, nbytes, stream=None):
+        self._check(self.lib.ray_b200_copy_to_host_async(self.handle, C.c_void_p(int(stream) if stream else None), C.c_void_p(int(host_ptr)),
+                                                         C.c_void_p(int(dev_ptr)), int(nbytes)))
 
     def detile(self, gathered_dev, out_pix_dev, h, w, world):
         self._check(self.lib.ray_b200_detile(self.handle, _ptr(gathered_dev), _ptr(out_pix_dev), int(h), int(w), int(world)))

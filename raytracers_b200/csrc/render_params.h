@@ -43,8 +43,12 @@ struct RenderParams {
   int32_t chunk_stride_inv;  // chunk_stride * chunk_stride_inv = 1 (mod n_chunks): position of a tile chunk in the claim sequence
   int32_t probes_per_tile, probe_segments;
   float4 *sample_buf;    // warp-queue kernel, spp > 1: [CTAs][warps][kWqRing][spp] finished-sample colours (else NULL)
-  // persistent-threads work cursor and optional work counters
+  // persistent-threads work cursor ([0]; [1] counts the warps that have left the kernel when frame_flag is set) and
+  // optional work counters
   int32_t *work_cursor;
+  // peer-frame protocol (NULL = off): out_pix may be a peer device's frame; the last warp to leave the kernel bumps
+  // *frame_flag (system scope) after a system-wide fence, so the consumer knows this rank's pixels have landed
+  uint32_t *frame_flag;
   unsigned long long *counters;  // [4] segments, node_steps, box_tests, leaf_tests (counting kernels only)
   // diagnostic (NULL unless tracing): [0] = earliest CTA start, [1 + cta * warps + warp] = that warp's exit, in
   // %globaltimer ns — shows how long the SMs sit idle behind the frame's last paths (warp-queue kernel only)
@@ -75,10 +79,20 @@ struct LaunchConfig {
   int wq_refill;       // warp-queue kernel, spread mode: hand out samples when at least this many slots are idle
   int wq_packet;       // warp-queue kernel: node steps with at least this many lanes are done packet-style (0 = never)
   int wq_ncap;         // warp-queue kernel: cap on the node-queue capacity (0 = the proved bound, at most 1024)
+  int lw_slots;        // lane-walk kernel: path slots per warp (32 lanes walk, the rest wait for / come from shading)
+  int lw_idle_min;     // lane-walk kernel: with the ready list empty, shade as soon as this many lanes have nothing to walk
+  int lw_passes;       // lane-walk kernel: refill passes per shading phase
+  int max_dynamic_smem;  // the device's opt-in shared-memory limit (kernels opt in on first launch)
 };
 
-void launch_render(const RenderParams &p, const LaunchConfig &lc, const WavefrontBuffers *wf, cudaStream_t stream,
-                   int64_t *launches);
+cudaError_t launch_render(const RenderParams &p, const LaunchConfig &lc, const WavefrontBuffers *wf, cudaStream_t stream,
+                          int64_t *launches);
+// per translation unit: K5 (render_lanewalk.cu) and the alternatives K1 / K2 / K4 (render_alt_kernels.cu; a product
+// build without RAYB200_ALL_KERNELS returns cudaErrorNotSupported)
+cudaError_t launch_lanewalk(const RenderParams &p, const LaunchConfig &lc, cudaStream_t stream, int64_t *launches);
+cudaError_t launch_alt_kernel(const RenderParams &p, const LaunchConfig &lc, const WavefrontBuffers *wf, cudaStream_t stream,
+                              int64_t *launches);
+bool alt_kernels_built();
 // Probe pass + sort that produce RenderParams::tile_order (see render_kernels.cu).  All buffers are device memory.
 struct TileOrderBuffers {
   uint32_t *keys, *keys_sorted;   // [local_tiles]
@@ -93,6 +107,10 @@ inline int tile_order_key_bits(int32_t n_chunks) {  // keys are positions < n_ch
   return bits;
 }
 void launch_tile_order(const RenderParams &p, const TileOrderBuffers &b, cudaStream_t stream, int64_t *launches);
+// peer-frame flags (render_kernels.cu): 1-thread kernels on `stream`
+void launch_flag_wait(uint32_t *flag, uint32_t value, long long timeout_ns, unsigned long long *timeouts, cudaStream_t stream);
+void launch_flag_set(uint32_t *flag, uint32_t value, cudaStream_t stream);
+void launch_flag_bump(uint32_t *flag, cudaStream_t stream);  // for the kernels that do not signal themselves
 void launch_count_work(const RenderParams &p, cudaStream_t stream, int64_t *launches);
 void launch_detile(const int32_t *gathered, int32_t *out, int64_t H, int64_t W, int32_t world, int64_t tiles_padded,
                    cudaStream_t stream, int64_t *launches);
@@ -135,6 +153,12 @@ __host__ __device__ inline size_t sq_warp_bytes(int k, int ncap) {
 }
 
 
-cudaError_t configure_kernels(int max_dynamic_smem);
+// lane-walk kernel (K5): private DFS stack entries per lane (<= one deferred sibling per level) and per-warp bytes:
+// R slots x (4 float4 + best t / leaf + item + meta), sample ring, leaf-item stack, [scap][32] DFS stacks, 3 slot lists
+__host__ __device__ inline int lw_stack_capacity(int max_depth) { return max_depth + 1 < 4 ? 4 : max_depth + 1; }
+__host__ __device__ inline size_t lw_warp_bytes(int slots, int scap) {
+  const size_t r = (size_t)slots;
+  return (r * (16 * 4 + 4 * 4) + 2 * kWqRing * 4 + kWqLeafStack * 4 + (size_t)scap * 128 + ((3 * r + 15) & ~(size_t)15) + 127) & ~(size_t)127;
+}
 
 }  // namespace rayb200

@@ -132,3 +132,112 @@ class ShardedRenderer:
                 self.ctx.detile(gathered.data_ptr(), frame.data_ptr(), h, w, self.world)
                 frames.append(frame)
         return frames if self.rank == 0 else None
+
+
+class PeerFrameRenderer:
+    """The gather fused into the render kernel (include/ray_b200.h, "peer-memory frames").
+
+    Rank 0 owns a ring of `slots` frames (int32[h][w] each, cudaMalloc + CUDA IPC) followed by two 32-bit flags per slot;
+    every other rank maps that allocation over NVLink.  A frame is rendered by ALL ranks at once, each with its shard set
+    and rank 0's frame slot as the row-major output: the kernels' pixel stores land in rank 0's memory, and the last warp
+    of each rank's kernel bumps the slot's `done` flag.  Rank 0's copy stream waits for `done` to reach world x (use count),
+    copies the frame to page-locked host memory and releases the slot by setting `ack`; the producers' next render into
+    that slot waits for the ack.  No tile buffers, no ncclGather, no de-tiling kernel, no host synchronisation between
+    frames: rendering, the NVLink transfer and the device-to-host copy of consecutive frames overlap.
+
+    torch is used for the copy stream / pinned host buffers and for ONE object broadcast of the IPC handle at set-up."""
+
+    FLAG_BYTES = 256  # per slot: done flag at +0, ack flag at +128 (separate lines)
+
+    def __init__(self, ctx, rank, world, h, w, slots=4, group=None, same_process_base=None):
+        """same_process_base: tests only - the rank-0 renderer's `base` when several "ranks" are contexts of ONE process on
+        one GPU (a process cannot open its own IPC handle)."""
+        import torch
+
+        self.ctx, self.rank, self.world, self.h, self.w, self.slots = ctx, rank, world, h, w, slots
+        self.torch = torch
+        ctx.set_shard(rank, world)
+        self.frame_bytes = (h * w * 4 + 255) // 256 * 256
+        total = slots * (self.frame_bytes + self.FLAG_BYTES)
+        self.mapped = False
+        if rank == 0:
+            self.base, handle = ctx.ipc_alloc(total)
+        if same_process_base is not None:
+            if rank != 0:
+                self.base = same_process_base
+        elif world > 1:
+            import torch.distributed as dist
+            box = [handle if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0, group=group)
+            if rank != 0:
+                self.base = ctx.ipc_open(box[0])
+                self.mapped = True
+        self.uses = [0] * slots          # how often each slot has been rendered into
+        self.seq = 0
+        if rank == 0:
+            self.copy_stream = torch.cuda.Stream()
+            self.landed = torch.cuda.Event()   # recorded on the copy stream when the last consumed frame has fully arrived
+            self.host = [torch.empty((h, w), dtype=torch.int32, pin_memory=True) for _ in range(slots)]
+
+    def _slot(self, s):
+        frame = self.base + s * self.frame_bytes
+        flags = self.base + self.slots * self.frame_bytes + s * self.FLAG_BYTES
+        return frame, flags, flags + 128
+
+    def jobs(self, frames):
+        """frames: sequence of (prepared, spp).  Returns render_batch job dicts for the next len(frames) ring slots and
+        the slot numbers (call `consume` with them on rank 0 afterwards)."""
+        out, used = [], []
+        for prepared, spp in frames:
+            s = self.seq % self.slots
+            frame, done, ack = self._slot(s)
+            out.append(dict(prepared=prepared, h=self.h, w=self.w, spp=spp, out_dev=frame, done_flag=done,
+                            wait_flag=ack if self.uses[s] > 0 else None, wait_value=self.uses[s]))
+            self.uses[s] += 1
+            used.append(s)
+            self.seq += 1
+        return out, used
+
+    def render(self, frames):
+        """Enqueues the frames on every rank (one ray_b200_render_batch: two in flight) and, on rank 0, their hand-over
+        to host memory on the copy stream.  Returns the pinned host tensors on rank 0 (valid after `wait`), else None."""
+        jobs, used = self.jobs(frames)
+        self.ctx.render_batch(jobs)
+        return self.consume(used)
+
+    def consume(self, used):
+        if self.rank != 0:
+            return None
+        cs = self.copy_stream.cuda_stream
+        outs = []
+        for s in used:
+            frame, done, ack = self._slot(s)
+            self.ctx.flag_wait(done, self.world * self.uses[s], stream=cs)
+            self.landed.record(self.copy_stream)   # every rank's pixels of this frame are in rank 0's HBM
+            self.ctx.copy_to_host_async(self.host[s].data_ptr(), frame, self.h * self.w * 4, stream=cs)
+            self.ctx.flag_set(ack, self.uses[s], stream=cs)
+            outs.append(self.host[s])
+        return outs
+
+    def flag_timeouts_safe(self):
+        try:
+            return self.ctx.flag_timeouts()
+        except Exception:
+            return 0
+
+    def wait(self):
+        """Blocks until every frame handed to `consume` is in host memory (rank 0); raises if a flag wait timed out."""
+        if self.rank == 0:
+            self.copy_stream.synchronize()
+        self.ctx.sync()
+        if self.ctx.flag_timeouts():
+            raise RuntimeError("PeerFrameRenderer: a peer-frame flag wait timed out (a rank did not deliver its pixels)")
+
+    def close(self):
+        self.ctx.sync()
+        if self.rank == 0:
+            self.copy_stream.synchronize()
+            self.ctx.ipc_free(self.base)
+        elif self.mapped:
+            self.ctx.ipc_close(self.base)
+        self.base = None

@@ -46,7 +46,7 @@ def test_python_binding_covers_the_headers(R):
 def test_struct_layouts_match_the_library(R):
     """ctypes mirrors of the C structs have the size the library was compiled with (no GPU needed)."""
     lib = R.load_library()
-    assert ctypes.sizeof(R.RenderJob) == lib.ray_b200_render_job_size() == 48
+    assert ctypes.sizeof(R.RenderJob) == lib.ray_b200_render_job_size() == 72
 
 
 def _compile(src, out, extra=()):

@@ -10,7 +10,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-KERNELS = ["mega", "persistent", "wavefront", "warpqueue", "streamqueue"]
+KERNELS = ["mega", "persistent", "wavefront", "warpqueue", "streamqueue", "lanewalk"]
 
 
 def sha(a):
@@ -198,7 +198,7 @@ def test_heavy_first_claim_order_is_invisible(R, oracle, golden, heavy_first):
     assert_same(gpu_frame(R, "rgbbox", 3, 5, "warpqueue", spp=2, heavy_first=heavy_first), w4, "single tile")
 
 
-@pytest.mark.parametrize("kernel", ["warpqueue", "persistent", "mega", "wavefront", "streamqueue"])
+@pytest.mark.parametrize("kernel", ["warpqueue", "lanewalk", "persistent", "mega", "wavefront", "streamqueue"])
 def test_render_batch_two_frames_in_flight(R, oracle, kernel):
     """ray_b200_render_batch: frames of different scenes / sizes / spp submitted as one stream-ordered operation (two in
     flight) are bit-identical to the oracle, in the row-major and the compact shard layout, with and without float output."""
@@ -270,6 +270,103 @@ def test_warpqueue_deep_tree_and_many_samples(R, oracle):
         assert_same(ctx.render_host(h, w, pr, spp=spp), want, "300 spp, spread")
 
 
+
+@pytest.mark.parametrize("tuning", [dict(), dict(lw_slots=32), dict(lw_slots=64, lw_warps=20), dict(lw_warps=1, lw_slots=40), dict(lw_warps=7, lw_idle_min=1),
+                                    dict(lw_idle_min=32, lw_passes=1), dict(lw_passes=8, lw_slots=56, lw_warps=24), dict(wq_spread=0)])
+def test_lanewalk_variants(R, oracle, golden, tuning):
+    """K5 (lane-owned traversals, slot lists, dense shading batches): reference PNGs, partial tiles at spp > 1 with the float
+    framebuffer, the compact sharded layout, a deep tree with duplicate Morton codes, equal-t ties, a sample count larger
+    than a ring round - over slot counts, warp counts and the shading / refill thresholds.  wq_spread=0 at spp > 1 must
+    fall back to the warp-queue kernel (K5 only runs spread or 1-spp frames) and still be exact."""
+    import torch
+    from raytracers_b200 import distributed as D
+    for name in ("rgbbox_500", "irreg_500"):
+        want, _ = golden[name]
+        assert_same(gpu_frame(R, name.split("_")[0], 500, 500, "lanewalk", **tuning), want, f"lanewalk {tuning} {name} vs reference PNG")
+    h, w, spp = 45, 83, 5
+    want, want_rgb, _ = oracle.Scene.rgbbox().prepare(h, w).render(h, w, spp=spp, want_rgb=True)
+    with R.Context(kernel="lanewalk", **tuning) as ctx:
+        pr = ctx.prepare_scene(h, w, ctx.rgbbox())
+        pix, rgb = ctx.render_host(h, w, pr, spp=spp, want_rgb=True)
+        assert_same(pix, want, f"lanewalk {tuning} spp 5")
+        np.testing.assert_array_equal(rgb.view(np.uint32), want_rgb.view(np.uint32))
+        world = 3
+        padded = D.tile_layout(h, w, world)[3]
+        for rank in range(world):
+            tiles = torch.empty((padded, 32), dtype=torch.int32, device="cuda")
+            ctx.set_shard(rank, world)
+            ctx.render_shard_into(tiles.data_ptr(), h, w, pr, spp=spp)
+            ctx.sync()
+            np.testing.assert_array_equal(tiles.cpu().numpy(), D.extract_rank_tiles(want, rank, world))
+    w3, _, _ = oracle.render_scene("random", 64, 96, n=60000, seed=3)
+    assert_same(gpu_frame(R, "random", 64, 96, "lanewalk", n=60000, seed=3, **tuning), w3, f"lanewalk {tuning} deep tree")
+    w4, _, _ = oracle.Scene.irreg().prepare(24, 40).render(24, 40, spp=300)
+    assert_same(gpu_frame(R, "irreg", 24, 40, "lanewalk", spp=300, **tuning), w4, f"lanewalk {tuning} 300 spp")
+    w5, _, _ = oracle.Scene.rgbbox().prepare(3, 5).render(3, 5, spp=2)
+    assert_same(gpu_frame(R, "rgbbox", 3, 5, "lanewalk", spp=2, **tuning), w5, "single tile")
+
+
+def test_lanewalk_deep_tree_and_trace(R, oracle):
+    """150 K random spheres (tree depth >= 20: deeper private stacks, fewer slots fit) and the warp-exit trace."""
+    n, h, w = 150000, 64, 96
+    want, _, _ = oracle.render_scene("random", h, w, n=n, seed=11)
+    with R.Context(kernel="lanewalk") as ctx:
+        ctx.trace_warps(True)
+        pr = ctx.prepare_scene(h, w, ctx.scene_random(n, 11))
+        assert pr.info()["max_depth"] >= 20
+        assert_same(ctx.render_host(h, w, pr), want, "lanewalk deep tree, 1 spp")
+        t = ctx.warp_trace()
+        assert t.size % 148 == 0 and (t >= 0).all() and t.max() < 1e6
+
+
+
+@pytest.mark.parametrize("kernel", ["warpqueue", "lanewalk", "mega"])
+def test_peer_frame_renderer_on_one_gpu(R, oracle, kernel):
+    """The fused render+gather protocol (include/ray_b200.h "peer-memory frames") with the "ranks" emulated as contexts of
+    one process on one GPU: every rank writes its own pixels straight into rank 0's row-major frame slot, the last warp of
+    each kernel bumps the slot's done flag, rank 0's copy stream waits for world x uses, copies out and acknowledges.  More
+    frames than ring slots (back-pressure through the ack flags); frames must equal the oracle's."""
+    import torch
+    from raytracers_b200 import distributed as D
+    h, w, world = 45, 83, 3
+    frames = [("rgbbox", 1), ("irreg", 5), ("rgbbox", 5), ("irreg", 1), ("rgbbox", 2)]
+    want = {f: getattr(oracle.Scene, f[0])().prepare(h, w).render(h, w, spp=f[1])[0] for f in frames}
+    ctxs = [R.Context(kernel=kernel) for _ in range(world)]
+    try:
+        prep = [{n: c.prepare_scene(h, w, c.scene(n)) for n in ("rgbbox", "irreg")} for c in ctxs]
+        rr = [D.PeerFrameRenderer(ctxs[0], 0, world, h, w, slots=2, same_process_base=0)]
+        rr += [D.PeerFrameRenderer(ctxs[r], r, world, h, w, slots=2, same_process_base=rr[0].base) for r in range(1, world)]
+        got = []
+        for f in frames:                       # one frame at a time; rank order shuffled so rank 0 is not always first
+            order = list(range(world)) if len(got) % 2 == 0 else list(range(world))[::-1]
+            outs = None
+            for r in order:
+                o = rr[r].render([(prep[r][f[0]], f[1])])
+                outs = o if r == 0 else outs
+            rr[0].copy_stream.synchronize()
+            got.append(outs[0].numpy().copy())
+        for r in rr:
+            r.wait()
+        for f, g in zip(frames, got):
+            assert_same(g, want[f], f"peer frame {kernel} {f}")
+        # two frames per batch (two in flight), then a third batch that wraps the ring
+        for rep in range(2):
+            pair = [frames[1], frames[2]]
+            outs = None
+            for r in range(world):
+                o = rr[r].render([(prep[r][p[0]], p[1]) for p in pair])
+                outs = o if r == 0 else outs
+            rr[0].wait()
+            for p, o in zip(pair, outs):
+                assert_same(o.numpy(), want[p], f"peer frame batch {kernel} {p} rep {rep}")
+        assert ctxs[0].flag_timeouts() == 0
+        for r in rr[::-1]:
+            r.close()
+    finally:
+        for c in ctxs:
+            c.close()
+
+
 def test_headline_config_64spp_kernels_agree(R):
     """BASELINE configs[1]/[2] (1000x1000, 64 spp): too slow for the CPU oracle inside a test, so the kernels
     (lane-bound K1, sample-spread K3, pixel-bound K3) are checked against each other bit-for-bit."""
@@ -278,7 +375,8 @@ def test_headline_config_64spp_kernels_agree(R):
         b = gpu_frame(R, name, 1000, 1000, "warpqueue", spp=64)
         c = gpu_frame(R, name, 1000, 1000, "warpqueue", spp=64, wq_spread=0)
         d = gpu_frame(R, name, 1000, 1000, "streamqueue", spp=64)
-        assert sha(a) == sha(b) == sha(c) == sha(d), name
+        e = gpu_frame(R, name, 1000, 1000, "lanewalk", spp=64)
+        assert sha(a) == sha(b) == sha(c) == sha(d) == sha(e), name
 
 
 def test_custom_scenes_edge_cases(R, oracle):

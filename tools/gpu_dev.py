@@ -56,8 +56,40 @@ def main():
     ap.add_argument("--wq_packet", default="0")
     ap.add_argument("--wq_refill", default="1")
     ap.add_argument("--wq_ncap", default="0")
+    ap.add_argument("--grid", default="", help="generic sweep: 'kernel:key=v1|v2,key2=v3|v4;kernel2:...' (cartesian product per kernel); "
+                                               "replaces --kernels and the per-kernel option lists")
     a = ap.parse_args()
     rows = []
+    if a.grid:
+        for cfg in a.configs.split(","):
+            parts = cfg.split(":")
+            name, h, w, spp = parts[0], int(parts[1]), int(parts[2]), int(parts[3])
+            n = int(parts[4]) if len(parts) > 4 else None
+            ref_hash = None
+            for spec in a.grid.split(";"):
+                kernel, _, kv = spec.partition(":")
+                keys, vals = [], []
+                for item in (kv.split(",") if kv else []):
+                    k, _, v = item.partition("=")
+                    keys.append(k)
+                    vals.append([int(x) for x in v.split("|")])
+                for combo in itertools.product(*vals):
+                    tuning = dict(zip(keys, combo))
+                    t0 = time.time()
+                    try:
+                        med, best, hsh = run(name, h, w, spp, kernel, a.reps, n=n, **tuning)
+                    except R.RayError as e:
+                        print(json.dumps(dict(config=cfg, kernel=kernel, **tuning, error=str(e))), flush=True)
+                        continue
+                    ref_hash = ref_hash or hsh
+                    row = dict(config=cfg, kernel=kernel, **tuning, ms_median=round(med, 4), ms_best=round(best, 4), hash=hsh,
+                               same_as_first=(hsh == ref_hash), wall=round(time.time() - t0, 2))
+                    rows.append(row)
+                    print(json.dumps(row), flush=True)
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", f"dev_{a.tag}.json"), "w") as f:
+            json.dump(rows, f, indent=1)
+        return
     for cfg in a.configs.split(","):
         parts = cfg.split(":")
         name, h, w, spp = parts[0], int(parts[1]), int(parts[2]), int(parts[3])
