@@ -29,6 +29,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# the peer-frame path waits on flags with 1-thread kernels; give every stream its own hardware queue (must be set before CUDA starts)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 SCENES = ("rgbbox", "irreg")
 H = W = 1000

@@ -30,6 +30,10 @@ struct futhark_context_config {
   int32_t gpus = 1;  // > 1: this ONE process drives that many devices (RAY_GPUS; the drop-in multi-GPU mode of main.c)
   int32_t blocks_per_sm = 4, smem_budget = 48 * 1024, refill_min = 8, tail_from = 8;
   int32_t wq_warps = 0 /* 0 = per scene: 32, or 24 for trees far larger than the caches */, wq_k = 1, wq_spread = 1, wq_packet = -1, wq_refill = 1, wq_ncap = 512, permute = 1, host_build = 0;
+  int32_t stage_cap = -1;    // warp-queue / lane-walk kernels: cap (bytes) on the shared memory used for staging the tree; what is not
+                             // used stays L1 cache.  -1 = per scene: everything for trees the caches hold; for trees far larger, what
+                             // keeps the kernel's shared memory under the 196 KB carve-out (32 KB of L1 left)
+  int32_t wf_sort = 0;       // wavefront kernel, N4 experiment: re-sort the ray queue before bounces 1..wf_sort (0 = off)
   int32_t lw_slots = 0 /* 0 = as many (<= 64) as shared memory allows */, lw_warps = 0, lw_idle_min = 4, lw_passes = 4;
   int32_t heavy_first = 0;   // pull long-path tiles to the front of the claim order: 0 off (default: the probe pass costs more than the tail it saves on one GPU, see profiles/), 1/2/4 = probe pixels per tile, -1 = on when spp > 1
   int32_t probe_segments = 8;

@@ -123,9 +123,10 @@ int fill_params(futhark_context *ctx, const futhark_opaque_prepared_scene *p, in
     for (int attempt = 0; attempt < 2; attempt++) {
       const bool pk = want_packet != 0;
       per_warp = (int64_t)wq_warp_bytes(k, wq_node_capacity(k, p->max_depth, ctx->cfg.wq_ncap), pk);
-      // 32 warps hide latency best while the tree is cache-resident (rgbbox, irreg); the 1 M-sphere tree (64 MB of
-      // nodes) runs 8 % faster with 24 warps, i.e. more L1 per warp (profiles/r1_sweep_cta_size.json)
-      const int auto_warps = (int64_t)(p->n - 1) * 64 <= ((int64_t)8 << 20) ? 32 : 24;
+      // 32 warps hide latency best, also for the 1 M-sphere tree (64 MB of nodes) once its staging area is capped so
+      // that the SM keeps 32 KB of L1 (below; profiles/r2_sweep_stage_cap.json: 91.4 ms with 24 warps and everything
+      // staged -> 77.5 ms with 32 warps and 2 KB staged)
+      const int auto_warps = 32;
       wq_w = ctx->cfg.wq_warps < 1 ? auto_warps : (ctx->cfg.wq_warps > kWqMaxWarps ? kWqMaxWarps : ctx->cfg.wq_warps);
       while (wq_w > 1 && wq_w * per_warp + 8192 > (int64_t)ctx->max_smem_optin) wq_w--;
       if (want_packet >= 0) break;
@@ -158,6 +159,18 @@ int fill_params(futhark_context *ctx, const futhark_opaque_prepared_scene *p, in
     ctx->plan_wq_packet = 0;
   }
   ctx->plan_kernel = kern;
+  if (kern == RAY_B200_KERNEL_WARPQUEUE || kern == RAY_B200_KERNEL_LANEWALK) {
+    // Shared memory not used by the kernel stays L1: a tree far larger than the caches gains more from 60-100 KB of L1
+    // for its hot middle levels than from a few hundred more staged top nodes (profiles/r2_sweep_stage_cap.json)
+    const bool huge = (int64_t)(p->n - 1) * 64 > ((int64_t)8 << 20);
+    // the carve-out granule below the maximum is 196 KB: staying under it leaves the SM 32 KB of L1 instead of ~0
+    const int64_t queues = (int64_t)ctx->max_smem_optin - 512 - budget;
+    // (the driver reserves 1 KB of shared memory per CTA on top of what the kernel asks for; measured: with 32 warps'
+    // queues = 192 KB, 2 KB of staging runs the 1 M-sphere frame in 77.5 ms, 3 KB in 94.1 ms)
+    const int64_t under_196k = std::max<int64_t>(1024, (int64_t)196 * 1024 - 2048 - queues);
+    const int64_t cap = ctx->cfg.stage_cap >= 0 ? ctx->cfg.stage_cap : (huge ? under_196k : budget);
+    budget = std::min<int64_t>(budget, std::max<int64_t>(cap, 256));
+  }
   int64_t nodes_fit = std::max<int64_t>(0, budget / 64);
   P.smem_nodes = (int32_t)std::min<int64_t>(P.n_inner, nodes_fit);
   const int64_t left = budget - (int64_t)P.smem_nodes * 64;
@@ -180,6 +193,7 @@ void free_wavefront(futhark_context *ctx) {
   }
   if (b.qlen) cudaFree(b.qlen);
   if (b.accum) cudaFree(b.accum);
+  if (b.sort_keys) cudaFree(b.sort_keys);   // one block: keys, sorted keys, ids, order, cub temp
   memset(&b, 0, sizeof b);
 }
 
@@ -187,7 +201,7 @@ void free_wavefront(futhark_context *ctx) {
 int ensure_wavefront(futhark_context *ctx, int64_t items) {
   WavefrontBuffers &b = ctx->wf;
   b.tail_from = ctx->cfg.tail_from;
-  if (b.capacity >= items) return 0;
+  if (b.capacity >= items && (ctx->cfg.wf_sort > 0) == (b.order != nullptr)) { b.sort_bounces = ctx->cfg.wf_sort; return 0; }
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   free_wavefront(ctx);
   b.tail_from = ctx->cfg.tail_from;
@@ -201,12 +215,25 @@ int ensure_wavefront(futhark_context *ctx, int64_t items) {
   CUDA_TRY(ctx, cudaMalloc(&b.qlen, 2 * (kMaxDepth + 2) * sizeof(int32_t)));
   b.cursor = b.qlen + (kMaxDepth + 2);
   b.capacity = items;
+  b.sort_bounces = 0;
+  if (ctx->cfg.wf_sort > 0 && wavefront_sort_bytes(items) > 0) {  // N4 experiment (RAY_WF_SORT = bounces to re-sort)
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t tmp = wavefront_sort_bytes(items), col = up((size_t)items * 4);
+    unsigned char *blk = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&blk, 4 * col + up(tmp)));
+    b.sort_keys = reinterpret_cast<uint32_t *>(blk);
+    b.sort_keys_out = reinterpret_cast<uint32_t *>(blk + col);
+    b.sort_ids = reinterpret_cast<int32_t *>(blk + 2 * col);
+    b.order = reinterpret_cast<int32_t *>(blk + 3 * col);
+    b.sort_tmp = blk + 4 * col;
+    b.sort_tmp_bytes = tmp;
+    b.sort_bounces = ctx->cfg.wf_sort;
+  }
   return 0;
 }
 
 // Enqueues one frame on lane `lane_id` (0 = the context's stream).  `timed`: bracket it with the context's timing events.
-// Peer-frame protocol of one frame (include/ray_b200.h): wait for *wait_flag >= wait_value before the kernel, bump
-
+// `ff`: peer-frame protocol of the frame (api_internal.h).
 int do_render(futhark_context *ctx, RenderParams &P, int lane_id, bool timed, const FrameFlags *ff) {
   futhark_context::Lane &L = ctx->lanes[lane_id];
   if (lane_id == 0) L.stream = ctx->stream;

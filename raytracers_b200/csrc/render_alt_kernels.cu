@@ -3,6 +3,7 @@
 // stream queue (K3 without rounds).  Compiled into libray_b200_all.so (-DRAYB200_ALL_KERNELS: the library the test-suite
 // loads for these kernels); the product library libray_b200.so carries only K0 / K3 / K5 and reports an error for the
 // others, so it stays small and futhark_context_new stays fast.
+#include <cub/cub.cuh>
 #include "render_common.cuh"
 
 namespace rayb200 {
@@ -99,7 +100,7 @@ template <bool kAllNodes, bool kSpheres>
 __global__ void __launch_bounds__(256, 2) wavefront_bounce_kernel(const __grid_constant__ RenderParams P,
                                                                    const __grid_constant__ WavefrontBuffers B,
                                                                    const int bounce, const int sample,
-                                                                   const int run_to_end) {
+                                                                   const int run_to_end, const int use_order) {
   const long long total64 = P.local_tiles * kTilePixels;
   const int n_in = bounce == 0 ? (int)total64 : B.qlen[bounce];
   if ((long long)blockIdx.x * 32 >= n_in) return;  // nothing for this CTA: skip the staging too
@@ -130,7 +131,8 @@ __global__ void __launch_bounds__(256, 2) wavefront_bounce_kernel(const __grid_c
         if (active) r = primary_ray(P, i, j, sample);
         else if (P.tile_major && last_sample) P.out_pix[idx] = 0;
       } else {
-        const float4 a = B.ray_o[qi][idx], d = B.ray_d[qi][idx], l = B.light[qi][idx];
+        const int src = use_order ? B.order[idx] : idx;  // N4 experiment: trace the queue in (octant, Morton) order
+        const float4 a = B.ray_o[qi][src], d = B.ray_d[qi][src], l = B.light[qi][src];
         r.o = v3(a.x, a.y, a.z);
         r.d = v3(d.x, d.y, d.z);
         light = v3(l.x, l.y, l.z);
@@ -514,9 +516,47 @@ __global__ void __launch_bounds__(kWqMaxThreads, 1) render_streamqueue_kernel(co
   }
 }
 
+// N4 experiment: sort key of queue entry i for `bounce` = direction octant (3 bits) | 29-bit Morton code of the origin
+// normalised to the root box; entries past the queue's length sort last.
+__device__ __forceinline__ uint32_t spread10(uint32_t v) {
+  v = (v * 0x00010001u) & 0xFF0000FFu;
+  v = (v * 0x00000101u) & 0x0F00F00Fu;
+  v = (v * 0x00000011u) & 0xC30C30C3u;
+  v = (v * 0x00000005u) & 0x49249249u;
+  return v;
+}
+__global__ void wavefront_sort_keys_kernel(const __grid_constant__ RenderParams P, const __grid_constant__ WavefrontBuffers B,
+                                           const int bounce) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B.capacity) return;
+  const int n = B.qlen[bounce], qi = bounce & 1;
+  uint32_t key = 0xffffffffu;
+  if (i < n) {
+    const float4 o = B.ray_o[qi][i], d = B.ray_d[qi][i];
+    const float sx = 1023.0f / fmaxf(P.root_box[3] - P.root_box[0], 1e-20f), sy = 1023.0f / fmaxf(P.root_box[4] - P.root_box[1], 1e-20f),
+                sz = 1023.0f / fmaxf(P.root_box[5] - P.root_box[2], 1e-20f);
+    const uint32_t x = (uint32_t)fminf(fmaxf((o.x - P.root_box[0]) * sx, 0.0f), 1023.0f);
+    const uint32_t y = (uint32_t)fminf(fmaxf((o.y - P.root_box[1]) * sy, 0.0f), 1023.0f);
+    const uint32_t z = (uint32_t)fminf(fmaxf((o.z - P.root_box[2]) * sz, 0.0f), 1023.0f);
+    const uint32_t m = (spread10(x) << 2) | (spread10(y) << 1) | spread10(z);
+    const uint32_t oct = (d.x < 0.0f ? 4u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 1u : 0u);
+    key = (oct << 29) | (m >> 1);
+    if (key == 0xffffffffu) key = 0xfffffffeu;
+  }
+  B.sort_keys[i] = key;
+  B.sort_ids[i] = (int32_t)i;
+}
+
 }  // namespace
 
 bool alt_kernels_built() { return true; }
+
+size_t wavefront_sort_bytes(int64_t items) {
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const int32_t *)nullptr,
+                                  (int32_t *)nullptr, (int)items, 0, 32);
+  return bytes;
+}
 
 cudaError_t launch_alt_kernel(const RenderParams &p, const LaunchConfig &lc, const WavefrontBuffers *wf, cudaStream_t stream,
                               int64_t *launches) {
@@ -533,12 +573,20 @@ cudaError_t launch_alt_kernel(const RenderParams &p, const LaunchConfig &lc, con
 #define RAYB200_WF(A, S)                                                                          \
   do {                                                                                            \
     e = opt_in_dynamic_smem<wavefront_bounce_kernel<A, S>>(lc.max_dynamic_smem);                  \
-    if (e == cudaSuccess) wavefront_bounce_kernel<A, S><<<(unsigned)want, threads, smem, stream>>>(p, *wf, b, s, rte); \
+    if (e == cudaSuccess) wavefront_bounce_kernel<A, S><<<(unsigned)want, threads, smem, stream>>>(p, *wf, b, s, rte, use_order); \
   } while (0)
     for (int s = 0; s < p.spp && e == cudaSuccess; s++) {
       cudaMemsetAsync(wf->qlen, 0, 2 * (kMaxDepth + 2) * sizeof(int32_t), stream);  // qlen and cursor are contiguous
       for (int b = 0; b <= tail && e == cudaSuccess; b++) {
         const int rte = b == tail;
+        const int use_order = (b >= 1 && b <= wf->sort_bounces && wf->order != nullptr) ? 1 : 0;
+        if (use_order) {  // N4 experiment: order the queue this bounce reads
+          wavefront_sort_keys_kernel<<<(unsigned)((wf->capacity + 255) / 256), 256, 0, stream>>>(p, *wf, b);
+          size_t tmp = wf->sort_tmp_bytes;
+          cub::DeviceRadixSort::SortPairs(wf->sort_tmp, tmp, wf->sort_keys, wf->sort_keys_out, wf->sort_ids, wf->order,
+                                          (int)wf->capacity, 0, 32, stream);
+          (*launches) += 2;
+        }
         if (all_nodes && sph) RAYB200_WF(true, true);
         else if (all_nodes) RAYB200_WF(true, false);
         else if (sph) RAYB200_WF(false, true);
@@ -598,6 +646,7 @@ cudaError_t launch_alt_kernel(const RenderParams &p, const LaunchConfig &lc, con
 #else   // product build: the alternatives are not compiled in
 
 bool alt_kernels_built() { return false; }
+size_t wavefront_sort_bytes(int64_t) { return 0; }
 
 cudaError_t launch_alt_kernel(const RenderParams &, const LaunchConfig &, const WavefrontBuffers *, cudaStream_t, int64_t *) {
   return cudaErrorNotSupported;

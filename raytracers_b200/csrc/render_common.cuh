@@ -44,12 +44,6 @@ __device__ __forceinline__ void ldg_node(const float4 *p, float4 &q0, float4 &q1
       : "=f"(q2.x), "=f"(q2.y), "=f"(q2.z), "=f"(q2.w), "=f"(q3.x), "=f"(q3.y), "=f"(q3.z), "=f"(q3.w)
       : "l"(p + 2));
 }
-__device__ __forceinline__ void prefetch_l1(const void *p) {
-#ifndef RAYB200_NO_TAILPF  // A/B builds only
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-#endif
-}
-
 struct GlobalScene {  // everything through the read-only path (L1/L2)
   const float4 *nodes, *geom;
   __device__ __forceinline__ void node(int cur, float4 &q0, float4 &q1, float4 &q2, float4 &q3) const {
@@ -70,13 +64,6 @@ struct StagedScene {  // top of the tree (BFS prefix) + optionally all spheres i
     } else {
       ldg_node(nodes + 4 * (size_t)cur, q0, q1, q2, q3);
     }
-  }
-  // tail mode: start a queued child's node on its way from L2 while its siblings are still being tested
-  __device__ __forceinline__ void prefetch_node(int cur) const {
-    if (!kAllNodes && cur >= smem_nodes) prefetch_l1(nodes + 4 * (size_t)cur);
-  }
-  __device__ __forceinline__ void prefetch_sphere(int i) const {
-    if (!kSpheres) prefetch_l1(geom + i);
   }
   __device__ __forceinline__ float4 sphere(int i) const { return kSpheres ? s_geom[i] : __ldg(geom + i); }
 };

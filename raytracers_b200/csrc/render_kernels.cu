@@ -396,15 +396,6 @@ __global__ void __launch_bounds__(kWqMaxThreads, 1) render_warpqueue_kernel(cons
         pr_leaf = rptr < 0;
         pl_node = hl && !pl_leaf;
         pr_node = hr && !pr_leaf;
-        // Tail mode (the work cursor has run out: this warp is on its last rays, few items per batch, the frame's end
-        // is a chain of dependent node steps): start the queued children's records on their way from L2 now.  In the
-        // bulk of a frame the same prefetch thrashes the 15 KB of L1 that the queues leave (profiles/r1_sweep_prefetch_ab.json).
-        if ((!kAllNodes || !kSpheres) && exhausted) {
-          if (pl_node) sc.prefetch_node(lptr);
-          if (pr_node) sc.prefetch_node(rptr);
-          if (pl_leaf) sc.prefetch_sphere(~lptr);
-          if (pr_leaf) sc.prefetch_sphere(~rptr);
-        }
       }
       __syncwarp();  // all pops have been read before anything is pushed over them
       ntop -= n;

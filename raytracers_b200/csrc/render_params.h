@@ -65,7 +65,15 @@ struct WavefrontBuffers {
   float4 *accum;      // per local item {sum.rgb, 0}: in-order sample accumulation when spp > 1
   int64_t capacity;   // items the queues can hold
   int32_t tail_from;  // bounce whose kernel runs the (few) surviving rays to completion
+  // N4 experiment (ray re-sorting between bounces, profiles/README.md): before bounces 1..sort_bounces the queue is
+  // ordered by (direction octant, Morton code of the origin in the root box) through an index array
+  int32_t sort_bounces;
+  uint32_t *sort_keys, *sort_keys_out;  // [capacity]
+  int32_t *sort_ids, *order;            // [capacity]; order[i] = queue entry to be traced i-th
+  void *sort_tmp;
+  size_t sort_tmp_bytes;
 };
+size_t wavefront_sort_bytes(int64_t items);  // cub temp storage for the re-sort (0 in builds without the alternative kernels)
 
 struct LaunchConfig {
   int kernel;          // ray_b200_kernel

@@ -175,9 +175,11 @@ class PeerFrameRenderer:
         self.uses = [0] * slots          # how often each slot has been rendered into
         self.seq = 0
         if rank == 0:
-            self.copy_stream = torch.cuda.Stream()
-            self.landed = torch.cuda.Event()   # recorded on the copy stream when the last consumed frame has fully arrived
-            self.host = [torch.empty((h, w), dtype=torch.int32, pin_memory=True) for _ in range(slots)]
+            cuda = torch.cuda.is_available()   # (the CPU protocol test drives this class with a stand-in context)
+            self.copy_stream = torch.cuda.Stream() if cuda else None
+            self.watch_stream = torch.cuda.Stream() if cuda else None
+            self.landed = torch.cuda.Event() if cuda else None   # recorded on the copy stream when the last consumed frame has fully arrived
+            self.host = [torch.empty((h, w), dtype=torch.int32, pin_memory=cuda) for _ in range(slots)]
 
     def _slot(self, s):
         frame = self.base + s * self.frame_bytes
@@ -198,22 +200,33 @@ class PeerFrameRenderer:
             self.seq += 1
         return out, used
 
-    def render(self, frames):
-        """Enqueues the frames on every rank (one ray_b200_render_batch: two in flight) and, on rank 0, their hand-over
-        to host memory on the copy stream.  Returns the pinned host tensors on rank 0 (valid after `wait`), else None."""
+    def submit(self, frames):
+        """Enqueues the frames on this rank (one ray_b200_render_batch: two in flight); returns their ring slots."""
         jobs, used = self.jobs(frames)
         self.ctx.render_batch(jobs)
-        return self.consume(used)
+        return used
+
+    def render(self, frames):
+        """submit + (rank 0) consume: the frames' hand-over to host memory on the copy stream.  Returns the pinned host
+        tensors on rank 0 (valid after `wait`), else None.
+        The flag waits are 1-thread spinning kernels: a wait only ever holds back work enqueued AFTER it on a stream that
+        shares its hardware queue, and it only depends on work enqueued BEFORE it (on this rank) and on the other ranks, so
+        one process per GPU cannot deadlock; several "ranks" inside ONE process (tests) must submit on all of them before
+        any consume."""
+        return self.consume(self.submit(frames))
 
     def consume(self, used):
         if self.rank != 0:
             return None
-        cs = self.copy_stream.cuda_stream
+        cs = self.copy_stream.cuda_stream if self.copy_stream is not None else None
+        if self.watch_stream is not None:   # "all frames have landed" without the device-to-host copies in between
+            for s in used:
+                self.ctx.flag_wait(self._slot(s)[1], self.world * self.uses[s], stream=self.watch_stream.cuda_stream)
+            self.landed.record(self.watch_stream)   # every rank's pixels of these frames are in rank 0's HBM
         outs = []
         for s in used:
             frame, done, ack = self._slot(s)
             self.ctx.flag_wait(done, self.world * self.uses[s], stream=cs)
-            self.landed.record(self.copy_stream)   # every rank's pixels of this frame are in rank 0's HBM
             self.ctx.copy_to_host_async(self.host[s].data_ptr(), frame, self.h * self.w * 4, stream=cs)
             self.ctx.flag_set(ack, self.uses[s], stream=cs)
             outs.append(self.host[s])
@@ -227,8 +240,9 @@ class PeerFrameRenderer:
 
     def wait(self):
         """Blocks until every frame handed to `consume` is in host memory (rank 0); raises if a flag wait timed out."""
-        if self.rank == 0:
+        if self.rank == 0 and self.copy_stream is not None:
             self.copy_stream.synchronize()
+            self.watch_stream.synchronize()
         self.ctx.sync()
         if self.ctx.flag_timeouts():
             raise RuntimeError("PeerFrameRenderer: a peer-frame flag wait timed out (a rank did not deliver its pixels)")
@@ -236,7 +250,9 @@ class PeerFrameRenderer:
     def close(self):
         self.ctx.sync()
         if self.rank == 0:
-            self.copy_stream.synchronize()
+            if self.copy_stream is not None:
+                self.copy_stream.synchronize()
+                self.watch_stream.synchronize()
             self.ctx.ipc_free(self.base)
         elif self.mapped:
             self.ctx.ipc_close(self.base)

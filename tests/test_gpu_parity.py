@@ -339,10 +339,8 @@ def test_peer_frame_renderer_on_one_gpu(R, oracle, kernel):
         got = []
         for f in frames:                       # one frame at a time; rank order shuffled so rank 0 is not always first
             order = list(range(world)) if len(got) % 2 == 0 else list(range(world))[::-1]
-            outs = None
-            for r in order:
-                o = rr[r].render([(prep[r][f[0]], f[1])])
-                outs = o if r == 0 else outs
+            used = [rr[r].submit([(prep[r][f[0]], f[1])]) for r in order][0]   # all "ranks" first (see PeerFrameRenderer.render)
+            outs = rr[0].consume(used)
             rr[0].copy_stream.synchronize()
             got.append(outs[0].numpy().copy())
         for r in rr:
@@ -352,10 +350,8 @@ def test_peer_frame_renderer_on_one_gpu(R, oracle, kernel):
         # two frames per batch (two in flight), then a third batch that wraps the ring
         for rep in range(2):
             pair = [frames[1], frames[2]]
-            outs = None
-            for r in range(world):
-                o = rr[r].render([(prep[r][p[0]], p[1]) for p in pair])
-                outs = o if r == 0 else outs
+            used = [rr[r].submit([(prep[r][p[0]], p[1]) for p in pair]) for r in range(world)][0]
+            outs = rr[0].consume(used)
             rr[0].wait()
             for p, o in zip(pair, outs):
                 assert_same(o.numpy(), want[p], f"peer frame batch {kernel} {p} rep {rep}")
@@ -365,6 +361,16 @@ def test_peer_frame_renderer_on_one_gpu(R, oracle, kernel):
     finally:
         for c in ctxs:
             c.close()
+
+
+
+def test_wavefront_ray_resort_is_invisible(R, oracle):
+    """N4 experiment (RAY_WF_SORT): re-ordering the per-bounce ray queue by (direction octant, origin Morton code) only
+    changes the ORDER rays are traced in - frames stay bit-identical (1 spp, spp > 1 with the in-order accumulator, deep tree)."""
+    for name, h, w, spp, kw in (("rgbbox", 96, 128, 1, {}), ("irreg", 96, 128, 3, {}), ("random", 64, 96, 1, dict(n=60000, seed=3))):
+        want, _, _ = oracle.render_scene(name, h, w, spp=spp, **kw)
+        for bounces in (1, 4, 60):
+            assert_same(gpu_frame(R, name, h, w, "wavefront", spp=spp, wf_sort=bounces, **kw), want, f"{name} wf_sort={bounces}")
 
 
 def test_headline_config_64spp_kernels_agree(R):

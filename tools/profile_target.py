@@ -19,6 +19,8 @@ a = ap.parse_args()
 tuning = dict((k, int(v)) for k, v in (kv.split("=") for kv in a.tuning.split(",") if kv))
 with R.Context(kernel=a.kernel, **tuning) as ctx:
     pr = ctx.prepare_scene(a.size, a.size, ctx.scene(a.scene, n=a.n))
+    import json
+    print("WORK", json.dumps(dict(scene=a.scene, size=a.size, spp=a.spp, **ctx.count_work(a.size, a.size, pr, spp=a.spp))), flush=True)
     for _ in range(a.frames):
         img = ctx.render(a.size, a.size, pr, spp=a.spp)
         ctx.sync()
