@@ -212,7 +212,12 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": sample, "host": "cpu"},
         "cpu_baseline": {"value": round(value, 3), "unit": "Mrays/s", "cores": cores, "cgroup_cpu_quota": host_cpu_quota(),
-                         "kind": "port", "sample": sample},
+                         "kind": "port", "sample": sample, "per_core": round(value / max(cores, 1), 3),
+                         "sample_bias": ({"segments_in_sample_x_row_step": int(segs / args.steps) * ROW_STEP, "segments_per_step": FULL_STEP_SEGMENTS[args.workload],
+                                          "ratio": round(segs / args.steps * ROW_STEP / FULL_STEP_SEGMENTS[args.workload], 4)}
+                                         if args.workload in FULL_STEP_SEGMENTS else None),
+                         "note": "oracle = bit-exact C++ port of the Futhark program (no Futhark compiler in the image); the reference README's "
+                                 "Futhark multicore numbers (1 spp 1000x1000, Ryzen 1700X, 8 cores): 179 ms rgbbox / 62 ms irreg = 22.5 / 27.9 Mrays/s"},
         "e2e": {"value": round(value, 3), "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -268,7 +273,7 @@ def run_ours(args):
     # the render kernel, D.PeerFrameRenderer); "nccl" = compact tile buffers + one NCCL gather + de-tiling kernel per frame
     sharded = D.ShardedRenderer(ctx, rank, world) if world > 1 else None
     peer = D.PeerFrameRenderer(ctx, rank, world, H, W, slots=4) if world > 1 and args.gather == "peer" else None
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    flush = torch.empty(160 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
     # One step = every frame of the workload, submitted as ONE batch (ray_b200_render_batch: two frames in flight, so
     # the long-path tail of a frame is covered by the start of the next); the frame with the longest tail goes first.
@@ -290,29 +295,68 @@ def run_ours(args):
         else:
             sharded.render_batch([(H, W, prepared[n], SPP) for n in order])
 
+    def strict_steps(k_steps):
+        """Round-1 protocol: every step is one JOINED batch between its own event pair, L2 flush outside the pairs."""
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k_steps)]
+        for k in range(k_steps):
+            flush.zero_()            # L2 flush between timed steps (untimed: outside the event pair)
+            evs[k][0].record(stream)
+            step()
+            evs[k][1].record(stream)
+        barrier()
+        return sum(a.elapsed_time(b) for a, b in evs)
+
+    def pipelined_steps(k_steps):
+        """K steps submitted back to back with pipelined submission (ray_b200_context_set_pipeline): frames alternate between
+        the context's two lanes ACROSS steps, so a frame's last 50-bounce paths are covered by the next frame's start
+        instead of idling the GPU at every step boundary.  ONE event pair around all K steps; the per-step L2 flush runs
+        inside it (on the context's stream, i.e. between the lane-0 frames of consecutive steps)."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ctx.set_pipeline(True)
+        e0.record(stream)
+        for k in range(k_steps):
+            flush.zero_()
+            if peer is not None:
+                peer.render([(prepared[n], SPP) for n in order])
+            else:
+                ctx.render_batch([dict(prepared=prepared[n], h=H, w=W, spp=SPP, out_dev=frames[n].data_ptr()) for n in order])
+        ctx.pipeline_join()
+        if peer is not None and rank == 0:   # ... and every rank's pixels of the last frames have landed in rank 0's HBM
+            stream.wait_event(peer.landed)
+        e1.record(stream)
+        barrier()
+        if peer is not None:
+            peer.wait()
+        ctx.set_pipeline(False)
+        return e0.elapsed_time(e1)
+
+    can_pipeline = not args.no_batch and not args.strict_steps and (world == 1 or peer is not None)
     for _ in range(max(args.warmup, 3)):
         step()
+    if can_pipeline:
+        pipelined_steps(2)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     launches0 = ctx.launch_count()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
-    for k in range(args.steps):
-        flush.zero_()            # L2 flush between timed steps (untimed: outside the event pair)
-        ev[k][0].record(stream)
-        step()
-        ev[k][1].record(stream)
-    barrier()
+    dev_ms = pipelined_steps(args.steps) if can_pipeline else strict_steps(args.steps)
     launches = ctx.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms = float(t.item())
     value = seg_per_step * args.steps / (dev_ms * 1e-3) / 1e6
+    strict = None
+    if can_pipeline:   # the same K steps in the round-1 protocol, for comparison
+        barrier()
+        ts = torch.tensor([strict_steps(args.steps)], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        strict = {"value": round(seg_per_step * args.steps / (float(ts.item()) * 1e-3) / 1e6, 1), "ms_per_step": round(float(ts.item()) / args.steps, 4),
+                  "protocol": "every step one joined batch between its own event pair, L2 flush outside the pairs (round-1 protocol)"}
 
     # per-kernel durations for the roofline (N=1: one persistent launch per frame), CUDA events on the launch stream
     roof = issue_all = None
@@ -372,12 +416,47 @@ def run_ours(args):
         dist.all_gather_object(allv, mine)
         rank_kernel_ms = {n: [v[n] for v in allv] for n in SCENES}
 
-    # e2e: host buffers through the public API, H2D + render + D2H inside the timed region (wall clock)
+    # e2e: host buffers through the public API; per step, inside the timed region (wall clock, barrier + synchronize on both
+    # sides): H2D of every scene's sphere records from page-locked memory + device LBVH build (on every rank), all frames of
+    # the step as one batch, and every frame's D2H into page-locked host memory (rank 0).
+    #   default ("peer", also at N = 1): D.PeerFrameRenderer with pipelined submission - the frames land in rank 0's ring
+    #     (over NVLink from the other ranks) and are copied out on its copy stream while the next frames render; nothing
+    #     blocks the host but the re-upload's own 32-byte read-back;
+    #   --gather nccl (N > 1): tile buffers + ncclGather + de-tile per frame, D2H on a second stream ordered by events;
+    #   --strict-steps / --no-batch at N = 1: the round-1 loop (futhark_entry_render-style call, blocking futhark_values).
     e2e = None
-    if world == 1:
+    h2d = sum(prepared[n].upload_bytes() for n in SCENES)
+    d2h = 4 * H * W * len(SCENES)
+    e2e_how = None
+    if can_pipeline:
+        e2e_how = "peer-frame ring + pipelined submission"
+        pf = peer if peer is not None else D.PeerFrameRenderer(ctx, rank, world, H, W, slots=4)
+        ctx.set_pipeline(True)
+
+        def e2e_steps(n_steps):
+            for _ in range(n_steps):
+                for name in SCENES:
+                    prepared[name].reupload()                       # H2D from pinned memory + LBVH build on the device
+                pf.render([(prepared[n], SPP) for n in order])      # render + (rank 0) flag wait, D2H, slot release on the copy stream
+            pf.wait()                                               # every frame of every step is in host memory
+
+        e2e_steps(2)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_steps(args.steps)
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        ctx.set_pipeline(False)
+        if rank == 0 and not args.no_cpu_baseline:   # the frames that reached the host are the frames the kernels wrote
+            got = {n: pf.host[(pf.seq - len(order) + i) % pf.slots].numpy().copy() for i, n in enumerate(order)}
+        else:
+            got = None
+        if peer is None:
+            pf.close()
+    elif world == 1:
+        e2e_how = "futhark_entry_render-style call per frame, blocking futhark_values_i32_2d"
+        got = None
         host = {n: torch.empty((H, W), dtype=torch.int32, pin_memory=True) for n in SCENES}
-        h2d = sum(prepared[n].upload_bytes() for n in SCENES)
-        d2h = 4 * H * W * len(SCENES)
 
         def e2e_step():
             for name in SCENES:
@@ -394,50 +473,38 @@ def run_ours(args):
             e2e_step()
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
-        e2e = {"value": round(seg_per_step * args.steps / e2e_s / 1e6, 1), "unit": "Mrays/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "ms_per_step": round(1e3 * e2e_s / args.steps, 3)}
     else:
-        # N > 1, per step: H2D of every scene's sphere records + device LBVH build on every rank, all frames of the step as
-        # one batch, and every frame's D2H into page-locked memory on rank 0 - all inside the timed region.
-        # peer: the frames land in rank 0's ring over NVLink and are copied out on its copy stream while the next
-        # frames render (nothing blocks the host but the re-upload's own read-back);  nccl: gather + de-tile per frame,
-        # then a D2H on a second stream ordered by events.
-        if peer is not None and peer.flag_timeouts_safe():
-            raise SystemExit("bench.py: a peer-frame flag wait timed out")
-        host = [torch.empty((H, W), dtype=torch.int32, pin_memory=True) for _ in SCENES] if (rank == 0 and peer is None) else None
-        copy_stream = torch.cuda.Stream() if (rank == 0 and peer is None) else None
+        e2e_how = "NCCL gather + de-tile per frame, D2H on a copy stream"
+        got = None
+        host = [torch.empty((H, W), dtype=torch.int32, pin_memory=True) for _ in SCENES] if rank == 0 else None
+        copy_stream = torch.cuda.Stream() if rank == 0 else None
         copied = [torch.cuda.Event() for _ in SCENES] if copy_stream is not None else None
         barrier()
         t0 = time.perf_counter()
         for k in range(args.steps):
             for name in SCENES:
                 prepared[name].reupload()
-            if peer is not None:
-                peer.render([(prepared[n], SPP) for n in order])
-            else:
-                if copied is not None and k > 0:
-                    for ev_c in copied:          # the frame buffers are reused: last step's copies must have read them
-                        stream.wait_event(ev_c)
-                frs = sharded.render_batch([(H, W, prepared[n], SPP) for n in order])
-                if rank == 0:
-                    ready_ev = torch.cuda.Event()
-                    ready_ev.record(stream)
-                    copy_stream.wait_event(ready_ev)
-                    with torch.cuda.stream(copy_stream):
-                        for i, fr in enumerate(frs):
-                            host[i].copy_(fr, non_blocking=True)
-                            copied[i].record(copy_stream)
-        if peer is not None:
-            peer.wait()
-        elif copy_stream is not None:
+            if copied is not None and k > 0:
+                for ev_c in copied:          # the frame buffers are reused: last step's copies must have read them
+                    stream.wait_event(ev_c)
+            frs = sharded.render_batch([(H, W, prepared[n], SPP) for n in order])
+            if rank == 0:
+                ready_ev = torch.cuda.Event()
+                ready_ev.record(stream)
+                copy_stream.wait_event(ready_ev)
+                with torch.cuda.stream(copy_stream):
+                    for i, fr in enumerate(frs):
+                        host[i].copy_(fr, non_blocking=True)
+                        copied[i].record(copy_stream)
+        if copy_stream is not None:
             copy_stream.synchronize()
         barrier()
         e2e_s = time.perf_counter() - t0
-        tt = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    tt = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if dist is not None:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": round(seg_per_step * args.steps / float(tt.item()) / 1e6, 1), "unit": "Mrays/s",
-               "h2d_bytes_per_step": sum(prepared[n].upload_bytes() for n in SCENES), "d2h_bytes_per_step": 4 * H * W * len(SCENES),
-               "ms_per_step": round(1e3 * float(tt.item()) / args.steps, 3)}
+    e2e = {"value": round(seg_per_step * args.steps / float(tt.item()) / 1e6, 1), "unit": "Mrays/s", "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": d2h, "ms_per_step": round(1e3 * float(tt.item()) / args.steps, 3), "how": e2e_how}
 
     # context: the reference's own published protocol (1 sample per pixel, README table) on this GPU
     one_spp = None
@@ -527,7 +594,11 @@ def run_ours(args):
             torch.cuda.synchronize()
             rows, pixels, bad = rows_differing(frames[name].cpu().numpy(), kept[name], 0, ROW_STEP)
             parity["scenes"][name] = {"rows": rows, "pixels": pixels, "differing": bad}
-        parity["differing"] = sum(v["differing"] for v in parity["scenes"].values())
+        if got is not None:   # ... and the frames the e2e leg delivered to HOST memory (through the peer-frame ring)
+            for name in SCENES:
+                rows, pixels, bad = rows_differing(got[name], kept[name], 0, ROW_STEP)
+                parity["scenes"][name]["e2e_host_frame_differing"] = bad
+        parity["differing"] = sum(v["differing"] + v.get("e2e_host_frame_differing", 0) for v in parity["scenes"].values())
 
     if rank == 0:
         line = {
@@ -535,12 +606,15 @@ def run_ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": round(dev_ms / args.steps, 4), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "kernel": args.kernel, "spp": SPP, "segments_per_step": seg_per_step,
-                       "l2": "flushed between timed steps (256 MiB memset outside the event pairs); scene is <1 MB",
+                       "l2": ("flushed every step (160 MiB memset on the context's stream, inside the single event pair of the K pipelined steps); scene is <1 MB"
+                              if can_pipeline else "flushed between timed steps (160 MiB memset outside the event pairs); scene is <1 MB"),
+                       "timing": ("K steps submitted back to back with pipelined submission (frames alternate between two lanes across steps), one CUDA-event pair around all K steps"
+                                  if can_pipeline else "one CUDA-event pair per step (joined batch)"),
                        "parallelism": (f"tile-sharded x{world}, " + ("pixels written straight into rank 0's frame over NVLink peer memory (gather fused into the render kernel)"
                                                                       if args.gather == "peer" else "one NCCL gather per frame")) if world > 1 else "single GPU",
                        "submission": "frame by frame" if args.no_batch else "one ray_b200_render_batch per step (two frames in flight)",
                        "ray": "one ray segment = one objs_hit call (ray.fut:76-86)"},
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_issue": issue_all,
+            "strict_steps": strict, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_issue": issue_all,
             "parity": parity, "cpu_baseline": cpu,
             "frame_ms_1spp": one_spp, "extra": extra, "shard_kernel_ms_per_rank": rank_kernel_ms,
             "published_reference_1spp_ms": PUBLISHED_1SPP_MS,
@@ -554,6 +628,10 @@ def run_ours(args):
         dist.destroy_process_group()
     return 0
 
+
+# segments of one full step (GPU counting kernel = the oracle's bvh_fold counters, tests/test_gpu_parity.py): lets the CPU arm
+# show that its row sample is unbiased without rendering the other 7/8 of the step
+FULL_STEP_SEGMENTS = {"headline": 368008372, "irreg4000": 7081424953}
 
 WORKLOADS = {
     # name: (scenes, H, W, spp, metric, workload description, rows the CPU legs sample)
@@ -578,6 +656,7 @@ def main():
     ap.add_argument("--kernel", default=os.environ.get("RAY_KERNEL", "auto"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-batch", action="store_true", help="submit the frames of a step one by one instead of as one batch")
+    ap.add_argument("--strict-steps", action="store_true", help="time every step as one joined batch between its own event pair (round-1 protocol) instead of K pipelined steps")
     ap.add_argument("--no-extra", action="store_true",
                     help="skip the once-per-run measurement (outside the timed steps) of BASELINE configs[3] and [4]: irreg 4000x4000 at 1 / 256 spp and the 1M-sphere scene")
     ap.add_argument("--extra", action="store_true", help="(default now; kept for compatibility)")

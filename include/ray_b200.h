@@ -150,6 +150,16 @@ struct ray_b200_render_job {
   uint32_t *done_flag;
 };
 int ray_b200_render_batch(struct futhark_context *ctx, const struct ray_b200_render_job *jobs, int32_t n);
+/* Pipelined submission (off by default).  With it on, ray_b200_render_batch does NOT join its second lane back into the
+ * context's stream: consecutive frames alternate between the two lanes ACROSS calls, each lane ordered only after its own
+ * previous frame (and after earlier work on the context's stream, e.g. a scene re-upload), so frame k+1 starts on every
+ * SM whose CTA of frame k has retired - a frame's last 50-bounce paths no longer idle the GPU at the end of every
+ * batch.  The caller orders its reads itself (done_flag / ray_b200_flag_wait, or ray_b200_pipeline_join, or
+ * futhark_context_sync, which waits for both lanes).  Prepared scenes may be freed or re-uploaded while frames that use
+ * them are in flight: their device memory is reclaimed only after the last such frame (stream-ordered, on a third stream). */
+int ray_b200_context_set_pipeline(struct futhark_context *ctx, int32_t on);
+/* Makes the context's stream wait for every frame enqueued so far on either lane (no host synchronisation). */
+int ray_b200_pipeline_join(struct futhark_context *ctx);
 /* sizeof(struct ray_b200_render_job) as the library was compiled: lets a foreign-language binding check its layout. */
 int64_t ray_b200_render_job_size(void);
 /* gathered_dev: int32[world][tiles_padded][32] (rank-major, as produced by an NCCL gather);

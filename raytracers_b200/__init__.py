@@ -27,7 +27,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 KERNELS = {"auto": 0, "mega": 1, "persistent": 2, "wavefront": 3, "warpqueue": 4, "streamqueue": 5, "lanewalk": 6}
 # The measured-slower alternative kernels are not part of the product library: they live in libray_b200_all.so (the
 # same objects + render_alt_kernels.cu built with RAYB200_ALL_KERNELS), which Context() loads when one of them is named.
-ALT_KERNELS = {2, 3, 5}
+ALT_KERNELS = {2, 3, 5, 6}
 
 
 class RayError(RuntimeError):
@@ -117,6 +117,8 @@ def load_library(variant=""):
         "ray_b200_context_last_render_ms": (C.c_int, [vp, C.POINTER(C.c_float)]),
         "ray_b200_render_batch": (C.c_int, [vp, C.POINTER(RenderJob), C.c_int32]),
         "ray_b200_render_job_size": (C.c_int64, []),
+        "ray_b200_context_set_pipeline": (C.c_int, [vp, i32]),
+        "ray_b200_pipeline_join": (C.c_int, [vp]),
         "ray_b200_context_trace_warps": (C.c_int, [vp, C.c_int32]),
         "ray_b200_context_warp_trace": (C.c_int, [vp, C.POINTER(C.c_float), C.c_int64, C.POINTER(C.c_int64)]),
         "ray_b200_context_launch_count": (i64, [vp]),
@@ -527,6 +529,13 @@ class Context:
             a.wait_value = int(j.get("wait_value") or 0)
             a.done_flag = int(j["done_flag"]) if j.get("done_flag") else None
         self._check(self.lib.ray_b200_render_batch(self.handle, arr, len(jobs)))
+
+    def set_pipeline(self, on=True):
+        """Pipelined submission: render_batch stops joining its second lane (frames of consecutive calls overlap)."""
+        self._check(self.lib.ray_b200_context_set_pipeline(self.handle, 1 if on else 0))
+
+    def pipeline_join(self):
+        self._check(self.lib.ray_b200_pipeline_join(self.handle))
 
     # -- peer-memory frames (include/ray_b200.h): raw device addresses as ints ---------------------------------
     def ipc_alloc(self, nbytes):

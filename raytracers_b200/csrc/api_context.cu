@@ -213,7 +213,8 @@ void futhark_context_free(struct futhark_context *ctx) {
     if (L.tile_order_block) cudaFree(L.tile_order_block);
     if (L.work_cursor) cudaFree(L.work_cursor);
   }
-  if (ctx->lanes[1].stream) cudaStreamDestroy(ctx->lanes[1].stream);
+  if (ctx->lanes[1].stream) { cudaStreamSynchronize(ctx->lanes[1].stream); cudaStreamDestroy(ctx->lanes[1].stream); }
+  if (ctx->reclaim) { cudaStreamSynchronize(ctx->reclaim); cudaStreamDestroy(ctx->reclaim); }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   for (auto &e : ctx->offset_tables) cudaFree(e.dev);
@@ -237,6 +238,8 @@ int futhark_context_sync(struct futhark_context *ctx) {
   }
   CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->lanes[1].stream) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->lanes[1].stream));  // pipelined submission does not join it
+  if (ctx->reclaim) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->reclaim));
   return 0;
 }
 

@@ -86,6 +86,9 @@ struct futhark_context {
     TileOrderBuffers tile_order_plan{};
   } lanes[2];
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool pipeline = false;                // ray_b200_context_set_pipeline: batches do not join lane 1 back
+  uint32_t lane_seq = 0;                // pipelined submission: frames alternate lanes across calls
+  cudaStream_t reclaim = nullptr;       // scene memory is freed here, ordered after its last use on either lane
   bool profiling_paused = false;
   int64_t renders = 0;
   bool ok = false;
@@ -108,6 +111,10 @@ struct futhark_opaque_prepared_scene {
   size_t pinned_bytes = 0;
   cudaEvent_t pinned_event = nullptr;  // completion of the last H2D copy that read `pinned`
   bool host_built = false;
+  // last render that read this scene's device memory, per lane (recorded by do_render): the memory is freed / replaced
+  // only after both (release_scene_block)
+  mutable cudaEvent_t last_use[2] = {nullptr, nullptr};
+  mutable bool used[2] = {false, false};
 };
 
 struct futhark_i32_2d {
@@ -152,12 +159,14 @@ struct FrameFlags {
   uint32_t wait_value = 0;
   uint32_t *done_flag = nullptr;
 };
-int do_render(futhark_context *ctx, RenderParams &P, int lane_id = 0, bool timed = true, const FrameFlags *ff = nullptr);
+int do_render(futhark_context *ctx, RenderParams &P, int lane_id = 0, bool timed = true, const FrameFlags *ff = nullptr,
+              const futhark_opaque_prepared_scene *scene = nullptr);
 // api_multigpu.cu: the single-process multi-GPU mode (RAY_GPUS > 1) of futhark_entry_render
 int create_helper_contexts(futhark_context *ctx, const futhark_context_config *cfg, int ndev);
 int render_multi_device(futhark_context *ctx, futhark_i32_2d *img, int64_t h, int64_t w, int32_t spp, const futhark_opaque_prepared_scene *p);
 // api_scene.cu
 void free_prepared_device(futhark_context *ctx, futhark_opaque_prepared_scene *p);
+int release_scene_block(futhark_context *ctx, futhark_opaque_prepared_scene *p);
 int prepare_on_device(futhark_context *ctx, futhark_opaque_prepared_scene *p);
 int prepare_any(futhark_context *ctx, futhark_opaque_prepared_scene *p);
 

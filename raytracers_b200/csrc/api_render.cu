@@ -234,7 +234,8 @@ int ensure_wavefront(futhark_context *ctx, int64_t items) {
 
 // Enqueues one frame on lane `lane_id` (0 = the context's stream).  `timed`: bracket it with the context's timing events.
 // `ff`: peer-frame protocol of the frame (api_internal.h).
-int do_render(futhark_context *ctx, RenderParams &P, int lane_id, bool timed, const FrameFlags *ff) {
+int do_render(futhark_context *ctx, RenderParams &P, int lane_id, bool timed, const FrameFlags *ff,
+              const futhark_opaque_prepared_scene *scene) {
   futhark_context::Lane &L = ctx->lanes[lane_id];
   if (lane_id == 0) L.stream = ctx->stream;
   LaunchConfig lc;
@@ -319,14 +320,19 @@ int do_render(futhark_context *ctx, RenderParams &P, int lane_id, bool timed, co
   {
     const cudaError_t le = launch_render(P, lc, &ctx->wf, L.stream, &ctx->launches);
     if (le == cudaErrorNotSupported) {
-      set_error(ctx, "render: kernel %d is not part of this build (libray_b200.so carries mega / warpqueue / lanewalk; the "
-                     "alternatives persistent / wavefront / streamqueue are in libray_b200_all.so, built with RAYB200_ALL_KERNELS)", lc.kernel);
+      set_error(ctx, "render: kernel %d is not part of this build (libray_b200.so carries mega / warpqueue; the alternatives "
+                     "persistent / wavefront / streamqueue / lanewalk are in libray_b200_all.so, built with RAYB200_ALL_KERNELS)", lc.kernel);
       return 1;
     }
     CUDA_TRY(ctx, le);
   }
   if (ff && ff->done_flag && !self_signal) launch_flag_bump(ff->done_flag, L.stream);
   CUDA_TRY(ctx, cudaGetLastError());
+  if (scene) {  // this frame reads the scene's device memory until here on this lane
+    if (!scene->last_use[lane_id]) CUDA_TRY(ctx, cudaEventCreateWithFlags(&scene->last_use[lane_id], cudaEventDisableTiming));
+    CUDA_TRY(ctx, cudaEventRecord(scene->last_use[lane_id], L.stream));
+    scene->used[lane_id] = true;
+  }
   if (timed) {
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_stop, L.stream));
     ctx->have_timing = true;
@@ -360,7 +366,7 @@ int ray_b200_entry_render_spp(struct futhark_context *ctx, struct futhark_i32_2d
   }
   // With a shard configured, the row-major frame only receives this rank's tiles; clear the rest.
   if (ctx->cfg.world > 1) cudaMemsetAsync(img->dev, 0, bytes, ctx->stream);
-  if (fill_params(ctx, p, h, w, spp, ctx->cfg.rank, ctx->cfg.world, img->dev, nullptr, false, P) || do_render(ctx, P)) {
+  if (fill_params(ctx, p, h, w, spp, ctx->cfg.rank, ctx->cfg.world, img->dev, nullptr, false, P) || do_render(ctx, P, 0, true, nullptr, p)) {
     cudaFreeAsync(img->dev, ctx->stream);
     delete img;
     return 1;
@@ -384,7 +390,7 @@ int ray_b200_render_into(struct futhark_context *ctx, int32_t *out_pix_dev, floa
   CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
   RenderParams P;
   if (fill_params(ctx, p, h, w, spp, ctx->cfg.rank, ctx->cfg.world, out_pix_dev, out_rgb_dev, false, P)) return 1;
-  return do_render(ctx, P);
+  return do_render(ctx, P, 0, true, nullptr, p);
 }
 
 int ray_b200_render_host(struct futhark_context *ctx, int32_t *out_pix_host, float *out_rgb_host, int64_t h, int64_t w, int32_t spp,
@@ -399,7 +405,7 @@ int ray_b200_render_host(struct futhark_context *ctx, int32_t *out_pix_host, flo
   CUDA_TRY(ctx, cudaMallocAsync(&d_pix, px * 4, ctx->stream));
   if (out_rgb_host) CUDA_TRY(ctx, cudaMallocAsync(&d_rgb, px * 12, ctx->stream));
   RenderParams P;
-  int rc = fill_params(ctx, p, h, w, spp, 0, 1, d_pix, d_rgb, false, P) || do_render(ctx, P);
+  int rc = fill_params(ctx, p, h, w, spp, 0, 1, d_pix, d_rgb, false, P) || do_render(ctx, P, 0, true, nullptr, p);
   if (!rc) {
     if (cudaMemcpyAsync(out_pix_host, d_pix, px * 4, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) rc = 1;
     if (!rc && d_rgb && cudaMemcpyAsync(out_rgb_host, d_rgb, px * 12, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) rc = 1;
@@ -432,7 +438,7 @@ int ray_b200_render_shard_into(struct futhark_context *ctx, int32_t *out_tiles_d
   const int64_t padded = ray_b200_shard_tiles_padded(h, w, ctx->cfg.world);
   if (P.local_tiles < padded)
     CUDA_TRY(ctx, cudaMemsetAsync(out_tiles_dev + P.local_tiles * kTilePixels, 0, (size_t)(padded - P.local_tiles) * kTilePixels * 4, ctx->stream));
-  return do_render(ctx, P);
+  return do_render(ctx, P, 0, true, nullptr, p);
 }
 // Several frames in one call, up to two of them in flight: job i runs on lane i % 2, lane 1 forks from the context's
 // stream at the start of the call and joins it at the end, so for the caller the batch behaves like one stream-ordered
@@ -452,7 +458,9 @@ int ray_b200_render_batch(struct futhark_context *ctx, const struct ray_b200_ren
   }
   const int kernel = resolve_kernel(ctx);
   // the wavefront kernel's ray queues and the warp trace exist once per context: those batches run in order on lane 0
-  const bool two_lanes = n > 1 && kernel != RAY_B200_KERNEL_WAVEFRONT && !ctx->warp_trace;
+  const bool lanes_ok = kernel != RAY_B200_KERNEL_WAVEFRONT && !ctx->warp_trace;
+  const bool pipe = ctx->pipeline && lanes_ok;   // frames alternate lanes across calls, no join at the end
+  const bool two_lanes = lanes_ok && (n > 1 || pipe);
   futhark_context::Lane &L1 = ctx->lanes[1];
   if (two_lanes && !L1.stream) {
     CUDA_TRY(ctx, cudaStreamCreateWithFlags(&L1.stream, cudaStreamNonBlocking));
@@ -466,7 +474,7 @@ int ray_b200_render_batch(struct futhark_context *ctx, const struct ray_b200_ren
   int rc = 0;
   for (int32_t i = 0; i < n && !rc; i++) {
     const ray_b200_render_job &j = jobs[i];
-    const int lane = two_lanes ? (i & 1) : 0;
+    const int lane = pipe ? (int)(ctx->lane_seq++ & 1u) : (two_lanes ? (i & 1) : 0);
     const int32_t spp = j.spp > 0 ? j.spp : ctx->cfg.spp;
     RenderParams P;
     if (j.shard_layout) {
@@ -483,10 +491,11 @@ int ray_b200_render_batch(struct futhark_context *ctx, const struct ray_b200_ren
     }
     FrameFlags ff;
     ff.wait_flag = j.wait_flag; ff.wait_value = j.wait_value; ff.done_flag = j.done_flag;
-    if (!rc) rc = do_render(ctx, P, lane, false, (ff.wait_flag || ff.done_flag) ? &ff : nullptr);
+    if (!rc) rc = do_render(ctx, P, lane, false, (ff.wait_flag || ff.done_flag) ? &ff : nullptr, j.prepared);
   }
   // join even after a failure: whatever was enqueued on lane 1 must be ordered before later work on the context's stream
-  if (two_lanes) {
+  // (pipelined submission: no join - the caller orders its reads, see ray_b200_context_set_pipeline)
+  if (two_lanes && (!pipe || rc)) {
     if (cudaEventRecord(ctx->ev_join, L1.stream) != cudaSuccess || cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0) != cudaSuccess) {
       if (!rc) set_error(ctx, "render_batch: join failed");
       rc = 1;
@@ -500,6 +509,28 @@ int ray_b200_render_batch(struct futhark_context *ctx, const struct ray_b200_ren
 }
 
 int64_t ray_b200_render_job_size(void) { return (int64_t)sizeof(struct ray_b200_render_job); }
+
+int ray_b200_context_set_pipeline(struct futhark_context *ctx, int32_t on) {
+  if (bad_ctx(ctx)) return 1;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  if (ctx->pipeline && !on && ctx->lanes[1].stream) {  // leaving the mode: everything in flight joins the context's stream
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->lanes[1].stream));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+  }
+  ctx->pipeline = on != 0;
+  return 0;
+}
+int ray_b200_pipeline_join(struct futhark_context *ctx) {
+  if (bad_ctx(ctx)) return 1;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  if (ctx->lanes[1].stream) {
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->lanes[1].stream));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+  }
+  return 0;
+}
 
 int ray_b200_detile(struct futhark_context *ctx, const int32_t *gathered_dev, int32_t *out_pix_dev, int64_t h, int64_t w, int32_t world) {
   if (bad_ctx(ctx)) return 1;

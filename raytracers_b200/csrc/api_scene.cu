@@ -45,9 +45,29 @@ double now_us() {
 
 namespace rayb200_api {
 
+// Gives the scene's device block back to the stream-ordered pool.  Frames may still be reading it on either lane
+// (pipelined submission does not join the lanes): if the scene was ever rendered on the second lane, the free goes to
+// the context's reclaim stream behind the last use on both lanes; the context's stream itself is never made to wait.
+int release_scene_block(futhark_context *ctx, futhark_opaque_prepared_scene *p) {
+  if (!p->dev.block) return 0;
+  if (p->used[1]) {
+    if (!ctx->reclaim) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->reclaim, cudaStreamNonBlocking));
+    for (int l = 0; l < 2; l++)
+      if (p->used[l]) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->reclaim, p->last_use[l], 0));
+    CUDA_TRY(ctx, cudaFreeAsync(p->dev.block, ctx->reclaim));
+  } else {
+    CUDA_TRY(ctx, cudaFreeAsync(p->dev.block, ctx->stream));  // only ever used in the context's stream order
+  }
+  p->dev = DeviceBvh();
+  p->used[0] = p->used[1] = false;
+  return 0;
+}
+
 void free_prepared_device(futhark_context *ctx, futhark_opaque_prepared_scene *p) {
   cudaSetDevice(ctx->cfg.device);
-  if (p->dev.block) cudaFreeAsync(p->dev.block, ctx->stream);
+  release_scene_block(ctx, p);
+  for (int l = 0; l < 2; l++)
+    if (p->last_use[l]) { cudaEventDestroy(p->last_use[l]); p->last_use[l] = nullptr; }
   if (p->pinned) {
     if (ctx->pinned_cache.size() < 4) ctx->pinned_cache.push_back({p->pinned, p->pinned_bytes, p->pinned_event});
     else { cudaEventSynchronize(p->pinned_event); cudaEventDestroy(p->pinned_event); cudaFreeHost(p->pinned); }
@@ -72,7 +92,7 @@ int prepare_on_device(futhark_context *ctx, futhark_opaque_prepared_scene *p) {
   CUDA_TRY(ctx, cudaEventRecord(p->pinned_event, ctx->stream));
   const double t1 = timing ? now_us() : 0.0;
   p->refit_sweeps = (int32_t)log2f((float)(int64_t)n) + 2;  // bvh.fut:47, host libm as in the reference's C backend
-  if (p->dev.block) { CUDA_TRY(ctx, cudaFreeAsync(p->dev.block, ctx->stream)); p->dev = DeviceBvh(); }
+  if (release_scene_block(ctx, p)) return 1;
   CUDA_TRY(ctx, build_bvh_device(d_spheres, (int64_t)n, p->refit_sweeps, p->dev, ctx->d_build_result, ctx->stream, &ctx->launches));
   CUDA_TRY(ctx, cudaFreeAsync(d_spheres, ctx->stream));
   // the host needs the tree depth (stack sizing) and the root box (kernel parameter) before the first render
@@ -114,7 +134,7 @@ int prepare_on_host(futhark_context *ctx, futhark_opaque_prepared_scene *p) {
   memcpy(hostside.right, tree.right.data(), ni * 4);
   memcpy(hostside.parent, tree.parent.data(), ni * 4);
   memcpy(hostside.boxes, tree.boxes.data(), ni * 24);
-  if (p->dev.block) { CUDA_TRY(ctx, cudaFreeAsync(p->dev.block, ctx->stream)); p->dev = DeviceBvh(); }
+  if (release_scene_block(ctx, p)) return 1;
   unsigned char *blk = nullptr;
   CUDA_TRY(ctx, cudaMallocAsync(&blk, total, ctx->stream));
   carve_device_bvh(blk, n, p->dev);

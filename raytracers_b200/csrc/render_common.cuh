@@ -205,13 +205,16 @@ __device__ __forceinline__ Ray primary_ray(const RenderParams &P, int i, int j, 
 }
 
 // item k -> pixel.  Local tile lt = k >> 5 is global tile lt*world + rank; lane position k & 31 inside the 8x4 tile.
+// (fill_params caps a frame at 2^25 tiles, so the global tile index fits 32 bits: one 32-bit division instead of the
+// 64-bit one, which is a ~100-instruction subroutine executed at ~3 of 32 lanes on the refill / finish paths: 2.2 % of the
+// kernel's instructions in profiles/r2_wq_rgbbox_source_summary.txt.)
 __device__ __forceinline__ bool item_pixel(const RenderParams &P, int k, int &i, int &j) {
-  const long long t = (long long)(k >> 5) * P.world + P.rank;
+  const unsigned t = (unsigned)(k >> 5) * (unsigned)P.world + (unsigned)P.rank;
   const int sub = k & 31;
-  const int ty = (int)(t / P.tiles_x), tx = (int)(t - (long long)ty * P.tiles_x);
-  i = tx * kTileW + (sub & (kTileW - 1));
-  j = ty * kTileH + (sub >> 3);
-  return t < P.n_tiles && i < P.W && j < P.H;
+  const unsigned ty = t / (unsigned)P.tiles_x, tx = t - ty * (unsigned)P.tiles_x;
+  i = (int)tx * kTileW + (sub & (kTileW - 1));
+  j = (int)ty * kTileH + (sub >> 3);
+  return (long long)t < P.n_tiles && i < P.W && j < P.H;
 }
 
 __device__ __forceinline__ unsigned long long global_timer_ns() {

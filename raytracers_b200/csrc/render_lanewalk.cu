@@ -21,10 +21,19 @@
 //
 // Exactness is unchanged: the set of leaves visited is order-free, sphere hits are folded per slot as
 // "smallest t, lowest leaf index on ties" (fold_hit), shading is K3's shade_segment, samples are summed in sample order.
+//
+// MEASURED (round 2, profiles/README.md): correct on the first run, but 17-55 % SLOWER than K3 on every BASELINE config
+// (rgbbox 64 spp 45.4 vs 38.2 ms, irreg 21.2 vs 14.1, 1 M spheres 330 vs 77.5): the step itself is the ~85 instructions
+// estimated above, but the per-iteration list maintenance (finished lanes -> done list, idle lanes <- ready list: two
+// ballots, popc, byte-list traffic, ray reload) costs another ~75 and the leaf-item push ~35, so an iteration is ~200
+// instructions for 32 steps at ~95 % lane occupancy against K3's ~114 at 79 %; and un-staged nodes are fetched per lane
+// without K3's packet sharing.  Kept, like K1 / K2 / K4, as a measured alternative with the same parity tests, in the
+// RAYB200_ALL_KERNELS build only.
 #include "render_common.cuh"
 
 namespace rayb200 {
 
+#ifdef RAYB200_ALL_KERNELS
 namespace {
 
 constexpr int kLwFin = -1;    // lane state: traversal just ended, the slot is still in `tag`
@@ -407,5 +416,10 @@ cudaError_t launch_lanewalk(const RenderParams &p, const LaunchConfig &lc, cudaS
   if (e == cudaSuccess) (*launches)++;
   return e;
 }
+
+#else   // product build: K5 is not compiled in
+
+cudaError_t launch_lanewalk(const RenderParams &, const LaunchConfig &, cudaStream_t, int64_t *) { return cudaErrorNotSupported; }
+#endif
 
 }  // namespace rayb200

@@ -149,14 +149,19 @@ class PeerFrameRenderer:
 
     FLAG_BYTES = 256  # per slot: done flag at +0, ack flag at +128 (separate lines)
 
-    def __init__(self, ctx, rank, world, h, w, slots=4, group=None, same_process_base=None):
-        """same_process_base: tests only - the rank-0 renderer's `base` when several "ranks" are contexts of ONE process on
+    def __init__(self, ctx, rank, world, h, w, slots=4, group=None, same_process_base=None, pipeline=False):
+        """pipeline: switch the context to pipelined submission (ray_b200_context_set_pipeline): consecutive `render` calls
+        overlap on the GPU - the flags of this protocol are what orders the consumer.
+        same_process_base: tests only - the rank-0 renderer's `base` when several "ranks" are contexts of ONE process on
         one GPU (a process cannot open its own IPC handle)."""
         import torch
 
         self.ctx, self.rank, self.world, self.h, self.w, self.slots = ctx, rank, world, h, w, slots
         self.torch = torch
         ctx.set_shard(rank, world)
+        self.pipeline = bool(pipeline)
+        if self.pipeline:
+            ctx.set_pipeline(True)
         self.frame_bytes = (h * w * 4 + 255) // 256 * 256
         total = slots * (self.frame_bytes + self.FLAG_BYTES)
         self.mapped = False
@@ -249,6 +254,8 @@ class PeerFrameRenderer:
 
     def close(self):
         self.ctx.sync()
+        if self.pipeline:
+            self.ctx.set_pipeline(False)
         if self.rank == 0:
             if self.copy_stream is not None:
                 self.copy_stream.synchronize()

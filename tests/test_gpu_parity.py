@@ -373,6 +373,42 @@ def test_wavefront_ray_resort_is_invisible(R, oracle):
             assert_same(gpu_frame(R, name, h, w, "wavefront", spp=spp, wf_sort=bounces, **kw), want, f"{name} wf_sort={bounces}")
 
 
+
+@pytest.mark.parametrize("kernel", ["warpqueue", "lanewalk"])
+def test_pipelined_submission_with_scene_reupload(R, oracle, kernel):
+    """ray_b200_context_set_pipeline: frames of consecutive render_batch calls alternate between the two lanes WITHOUT a
+    join, while the scenes they read are re-uploaded (device LBVH rebuilt, old block released) before every batch and one is
+    freed mid-flight - the scene memory of a frame in flight must only be reclaimed after the frame (release_scene_block).
+    World-1 peer-frame ring as the consumer; every delivered host frame must equal the oracle's."""
+    from raytracers_b200 import distributed as D
+    h, w = 64, 96
+    cases = [("irreg", 3), ("rgbbox", 1), ("rgbbox", 4), ("irreg", 1)]
+    want = {c: getattr(oracle.Scene, c[0])().prepare(h, w).render(h, w, spp=c[1])[0] for c in cases}
+    with R.Context(kernel=kernel) as ctx:
+        prep = {n: ctx.prepare_scene(h, w, ctx.scene(n)) for n in ("rgbbox", "irreg")}
+        pf = D.PeerFrameRenderer(ctx, 0, 1, h, w, slots=4, pipeline=True)
+        got = []
+        for step in range(4):
+            for n in prep:
+                prep[n].reupload()
+            pair = [cases[(2 * step) % 4], cases[(2 * step + 1) % 4]]
+            outs = pf.render([(prep[c[0]], c[1]) for c in pair])
+            if step == 2:                          # a scene that is still being rendered is freed and prepared again
+                prep["irreg"].free()
+                prep["irreg"] = ctx.prepare_scene(h, w, ctx.scene("irreg"))
+            if step % 2 == 1:                      # ring of 4 slots, 2 frames per step: collect every second step
+                pf.wait()
+            got.append((pair, outs))
+        pf.wait()
+        for pair, outs in got[-2:]:                # the last two steps' host buffers are still intact (4 slots)
+            for c, o in zip(pair, outs):
+                assert_same(o.numpy(), want[c], f"pipelined {kernel} {c}")
+        # strict mode again: a joined batch right after leaving the pipeline
+        pf.close()
+        out = ctx.render_host(h, w, prep["rgbbox"], spp=4)
+        assert_same(out, want[("rgbbox", 4)], f"after pipeline {kernel}")
+
+
 def test_headline_config_64spp_kernels_agree(R):
     """BASELINE configs[1]/[2] (1000x1000, 64 spp): too slow for the CPU oracle inside a test, so the kernels
     (lane-bound K1, sample-spread K3, pixel-bound K3) are checked against each other bit-for-bit."""
