@@ -29,7 +29,7 @@ struct futhark_context_config {
   int32_t rank = 0, world = 1;
   int32_t gpus = 1;  // > 1: this ONE process drives that many devices (RAY_GPUS; the drop-in multi-GPU mode of main.c)
   int32_t blocks_per_sm = 4, smem_budget = 48 * 1024, refill_min = 8, tail_from = 8;
-  int32_t wq_warps = 0 /* 0 = per scene: 32, or 24 for trees far larger than the caches */, wq_k = 1, wq_spread = 1, wq_packet = -1, wq_refill = 1, wq_ncap = 512, permute = 1, host_build = 0;
+  int32_t wq_warps = 0 /* 0 = per scene: 32, or 24 for trees far larger than the caches */, wq_k = 0 /* 0 = per scene: 2 when the whole scene fits shared memory next to 24 warps' queues, else 1 */, wq_spread = 1, wq_packet = -1, wq_refill = 1, wq_ncap = 512, permute = 1, host_build = 0;
   int32_t stage_cap = -1;    // warp-queue / lane-walk kernels: cap (bytes) on the shared memory used for staging the tree; what is not
                              // used stays L1 cache.  -1 = per scene: everything for trees the caches hold; for trees far larger, what
                              // keeps the kernel's shared memory under the 196 KB carve-out (32 KB of L1 left)
@@ -63,7 +63,7 @@ struct futhark_context {
   struct PinnedBlock { unsigned char *ptr; size_t bytes; cudaEvent_t last_use; };
   std::vector<PinnedBlock> pinned_cache;    // page-locked upload buffers of freed prepared scenes, reused by the next prepare_scene
   BvhBuildResult *d_build_result = nullptr, *h_build_result = nullptr;  // device scratch / page-locked host mirror
-  int32_t plan_wq_warps = 0, plan_wq_packet = 0, plan_lw_slots = 0, plan_kernel = 0;  // fill_params' plan for the frame being set up
+  int32_t plan_wq_warps = 0, plan_wq_packet = 0, plan_wq_k = 1, plan_wq_ncap = 512, plan_lw_slots = 0, plan_kernel = 0;  // fill_params' plan for the frame being set up
   // single-process multi-GPU (cfg.gpus > 1): one helper context per extra device; this context is rank 0 and owns them
   std::vector<futhark_context *> peers;
   bool is_peer = false;
@@ -139,6 +139,7 @@ void set_error(futhark_context *ctx, const char *fmt, ...);
   } while (0)
 
 inline bool bad_ctx(futhark_context *ctx) { return ctx == nullptr || !ctx->ok; }
+constexpr int kAutoK2Warps = 24, kAutoK2Ncap = 256;   // warp-queue kernel, wq_k = 0: the plan for scenes that fit shared memory whole
 constexpr size_t kSpreadBudget = (size_t)1 << 30;  // cap on the finished-sample buffer of the sample-spreading kernels
 
 inline int64_t tiles_total(int64_t h, int64_t w) { return ((h + kTileH - 1) / kTileH) * ((w + kTileW - 1) / kTileW); }

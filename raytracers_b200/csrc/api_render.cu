@@ -112,7 +112,22 @@ int fill_params(futhark_context *ctx, const futhark_opaque_prepared_scene *p, in
   if (kern == RAY_B200_KERNEL_WARPQUEUE) {
     // one CTA per SM: as many warps as asked for (<= 32) while their queues leave >= 8 KB for staging;
     // deep trees need bigger node stacks, so they get fewer warps
-    const int k = ctx->cfg.wq_k == 1 ? 1 : 2;
+    // Rays in flight per warp (32 K) and node-queue cap.  wq_k = 0 (default): K = 2 with kAutoK2Warps warps and a
+    // kAutoK2Ncap-entry node queue when the WHOLE scene (tree + spheres) still fits next to those queues - a round of 64
+    // rays has relatively fewer partial batches at its end than a round of 32 (rgbbox 64 spp 38.08 -> 36.84 ms,
+    // profiles/r2_sweep_k2.json) - and K = 1 with 32 warps otherwise (a scene that is only partly staged loses more from
+    // the staging space the bigger slots take: irreg 13.5 -> 25+ ms).
+    int k = ctx->cfg.wq_k == 2 ? 2 : 1;
+    int ncap_cfg = ctx->cfg.wq_ncap, warps_cfg = ctx->cfg.wq_warps;
+    if (ctx->cfg.wq_k == 0) {
+      const int64_t scene_bytes = 128 + (int64_t)(p->n - 1) * 64 + (int64_t)p->n * 16;
+      const int64_t q2 = (int64_t)kAutoK2Warps * (int64_t)wq_warp_bytes(2, wq_node_capacity(2, p->max_depth, kAutoK2Ncap), false);
+      if (q2 + scene_bytes + 512 + 128 <= (int64_t)ctx->max_smem_optin) {
+        k = 2;
+        if (warps_cfg < 1) warps_cfg = kAutoK2Warps;
+        if (ctx->cfg.wq_ncap == 512) ncap_cfg = kAutoK2Ncap;   // (512 = the configured default: not set by the caller)
+      }
+    }
     // Packet steps pay off when item-mode node fetches are expensive (part of the tree not staged in shared memory)
     // AND the rays a warp holds are coherent: samples of one pixel (spp > 1) or primary rays of a dense frame.
     // Measured: irreg 64 spp -19 %, irreg 4000^2 1 spp -12 %; rgbbox (fully staged) +1..2 %; 1000^2 1 spp +5 %.
@@ -122,12 +137,12 @@ int fill_params(futhark_context *ctx, const futhark_opaque_prepared_scene *p, in
     int64_t per_warp = 0, wq_w = 0;
     for (int attempt = 0; attempt < 2; attempt++) {
       const bool pk = want_packet != 0;
-      per_warp = (int64_t)wq_warp_bytes(k, wq_node_capacity(k, p->max_depth, ctx->cfg.wq_ncap), pk);
+      per_warp = (int64_t)wq_warp_bytes(k, wq_node_capacity(k, p->max_depth, ncap_cfg), pk);
       // 32 warps hide latency best, also for the 1 M-sphere tree (64 MB of nodes) once its staging area is capped so
       // that the SM keeps 32 KB of L1 (below; profiles/r2_sweep_stage_cap.json: 91.4 ms with 24 warps and everything
       // staged -> 77.5 ms with 32 warps and 2 KB staged)
       const int auto_warps = 32;
-      wq_w = ctx->cfg.wq_warps < 1 ? auto_warps : (ctx->cfg.wq_warps > kWqMaxWarps ? kWqMaxWarps : ctx->cfg.wq_warps);
+      wq_w = warps_cfg < 1 ? auto_warps : (warps_cfg > kWqMaxWarps ? kWqMaxWarps : warps_cfg);
       while (wq_w > 1 && wq_w * per_warp + 8192 > (int64_t)ctx->max_smem_optin) wq_w--;
       if (want_packet >= 0) break;
       const int64_t b = (int64_t)ctx->max_smem_optin - wq_w * per_warp - 512 - 128;
@@ -139,6 +154,8 @@ int fill_params(futhark_context *ctx, const futhark_opaque_prepared_scene *p, in
     if (budget < 256) { set_error(ctx, "render: warp-queue kernel does not fit shared memory (tree depth %d)", p->max_depth); return 1; }
     ctx->plan_wq_packet = want_packet > 32 ? 32 : want_packet;
     ctx->plan_wq_warps = (int32_t)wq_w;
+    ctx->plan_wq_k = k;
+    ctx->plan_wq_ncap = ncap_cfg;
   }
   if (kern == RAY_B200_KERNEL_LANEWALK) {
     // one CTA per SM: lw_warps warps (32 unless told otherwise) x lw_slots path slots each (48 unless told otherwise,
@@ -246,10 +263,10 @@ int do_render(futhark_context *ctx, RenderParams &P, int lane_id, bool timed, co
   lc.refill_min = ctx->cfg.refill_min;
   lc.tail_from = ctx->cfg.tail_from;
   lc.wq_warps = ctx->plan_wq_warps > 0 ? ctx->plan_wq_warps : 1;
-  lc.wq_k = ctx->cfg.wq_k == 1 ? 1 : 2;
+  lc.wq_k = ctx->plan_wq_k == 2 ? 2 : 1;
   lc.wq_refill = ctx->cfg.wq_refill < 1 ? 1 : (ctx->cfg.wq_refill > 32 ? 32 : ctx->cfg.wq_refill);
   lc.wq_packet = ctx->plan_wq_packet;
-  lc.wq_ncap = ctx->cfg.wq_ncap;
+  lc.wq_ncap = lc.kernel == RAY_B200_KERNEL_WARPQUEUE ? ctx->plan_wq_ncap : ctx->cfg.wq_ncap;
   lc.lw_slots = ctx->plan_lw_slots;
   lc.lw_idle_min = ctx->cfg.lw_idle_min;
   lc.lw_passes = ctx->cfg.lw_passes;

@@ -113,17 +113,18 @@ __global__ void __launch_bounds__(kWqMaxThreads, 1) render_warpqueue_kernel(cons
 
   constexpr int R = 32 * K;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // %lanemask_lt / %lanemask_gt: at 64 registers the compiler does not keep these masks live across the batch bodies, and
-  // re-reading a special register is one instruction where re-deriving them from the thread index was four (ncu: 1.6 %
-  // of the kernel's instructions on the gt mask alone)
-#ifndef RAYB200_OLD_LANEMASK
+  // Lane masks.  At 64 registers the compiler does not keep them live across the batch bodies; re-reading %lanemask_lt/gt
+  // is one instruction where re-deriving them from the thread index is four, but it also changes the register
+  // allocation: measured A/B (profiles/r2_sweep_kernel_ab.json) the special registers win on the packet variants
+  // (irreg 64 spp 13.88 -> 13.49 ms, 1 M spheres 77.6 -> 76.4) and lose on the fully staged one (rgbbox 38.05 -> 38.64).
   unsigned lt_mask, gt_mask;
-  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
-  asm("mov.u32 %0, %%lanemask_gt;" : "=r"(gt_mask));
-#else   // A/B builds only
-  const unsigned lt_mask = (1u << lane) - 1u;
-  const unsigned gt_mask = lane == 31 ? 0u : ~((2u << lane) - 1u);
-#endif
+  if constexpr (kPacket) {
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
+    asm("mov.u32 %0, %%lanemask_gt;" : "=r"(gt_mask));
+  } else {
+    lt_mask = (1u << lane) - 1u;
+    gt_mask = lane == 31 ? 0u : ~((2u << lane) - 1u);
+  }
   unsigned char *wbase = smem_raw + ((staging_bytes(P) + 127) & ~(size_t)127) + (size_t)warp * wq_warp_bytes(K, ncap, kPacket);
   float4 *ray_o = reinterpret_cast<float4 *>(wbase);   // {o.xyz, a = dot d d}
   float4 *ray_i = ray_o + R;                           // {1/d.xyz, 0}
