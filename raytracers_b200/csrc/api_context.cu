@@ -40,7 +40,7 @@ int parse_kernel(const char *v, int dflt) {
   return atoi(v);
 }
 
-const char *kTuningNames[] = {"kernel", "spp", "blocks_per_sm", "smem_budget", "refill_min", "tail_from", "wq_warps", "wq_k", "wq_spread", "wq_packet", "wq_refill", "wq_ncap", "wf_sort", "stage_cap", "lw_slots", "lw_warps", "lw_idle_min", "lw_passes", "permute", "heavy_first", "probe_segments", "host_build", "rank", "world", "gpus"};
+const char *kTuningNames[] = {"kernel", "spp", "blocks_per_sm", "smem_budget", "refill_min", "tail_from", "wq_warps", "wq_k", "wq_spread", "wq_packet", "wq_refill", "wq_ncap", "wf_sort", "learn_order", "long_path", "stage_cap", "lw_slots", "lw_warps", "lw_idle_min", "lw_passes", "permute", "heavy_first", "probe_segments", "host_build", "rank", "world", "gpus"};
 constexpr int kNumTuning = sizeof(kTuningNames) / sizeof(kTuningNames[0]);
 
 }  // namespace
@@ -78,6 +78,8 @@ int futhark_context_config_set_tuning_param(struct futhark_context_config *cfg, 
   else if (!strcmp(name, "wq_packet")) cfg->wq_packet = (int32_t)v;  // (size_t)-1 = decide per scene
   else if (!strcmp(name, "wq_ncap")) cfg->wq_ncap = (int32_t)v;
   else if (!strcmp(name, "wf_sort")) cfg->wf_sort = (int32_t)v;
+  else if (!strcmp(name, "learn_order")) cfg->learn_order = (int32_t)v;
+  else if (!strcmp(name, "long_path")) cfg->long_path = (int32_t)v;
   else if (!strcmp(name, "stage_cap")) cfg->stage_cap = (int32_t)v;  // (size_t)-1 = decide per scene
   else if (!strcmp(name, "lw_slots")) cfg->lw_slots = (int32_t)v;
   else if (!strcmp(name, "lw_warps")) cfg->lw_warps = (int32_t)v;
@@ -118,6 +120,8 @@ struct futhark_context *futhark_context_new(struct futhark_context_config *cfg) 
   ctx->cfg.wq_ncap = env_int("RAY_WQ_NCAP", ctx->cfg.wq_ncap);
   ctx->cfg.stage_cap = env_int("RAY_STAGE_CAP", ctx->cfg.stage_cap);
   ctx->cfg.wf_sort = env_int("RAY_WF_SORT", ctx->cfg.wf_sort);
+  ctx->cfg.learn_order = env_int("RAY_LEARN_ORDER", ctx->cfg.learn_order);
+  ctx->cfg.long_path = env_int("RAY_LONG_PATH", ctx->cfg.long_path);
   ctx->cfg.lw_slots = env_int("RAY_LW_SLOTS", ctx->cfg.lw_slots);
   ctx->cfg.lw_warps = env_int("RAY_LW_WARPS", ctx->cfg.lw_warps);
   ctx->cfg.lw_idle_min = env_int("RAY_LW_IDLE_MIN", ctx->cfg.lw_idle_min);
@@ -159,6 +163,7 @@ struct futhark_context *futhark_context_new(struct futhark_context_config *cfg) 
   if ((e = cudaMemset(ctx->counters, 0, 5 * sizeof(unsigned long long))) != cudaSuccess) return fail("cudaMemset", e);
   if ((e = cudaMalloc(&ctx->d_build_result, sizeof(BvhBuildResult))) != cudaSuccess) return fail("cudaMalloc", e);
   if ((e = cudaMallocHost(&ctx->h_build_result, sizeof(BvhBuildResult))) != cudaSuccess) return fail("cudaMallocHost", e);
+  if ((e = preload_default_kernels(ctx->max_smem_optin)) != cudaSuccess) return fail("loading the render kernels", e);
   // keep freed frames in the stream-ordered pool: futhark/main.c frees and re-allocates the image every run
   cudaMemPool_t pool;
   if (cudaDeviceGetDefaultMemPool(&pool, ctx->cfg.device) == cudaSuccess) {

@@ -35,6 +35,10 @@ struct futhark_context_config {
                              // keeps the kernel's shared memory under the 196 KB carve-out (32 KB of L1 left)
   int32_t wf_sort = 0;       // wavefront kernel, N4 experiment: re-sort the ray queue before bounces 1..wf_sort (0 = off)
   int32_t lw_slots = 0 /* 0 = as many (<= 64) as shared memory allows */, lw_warps = 0, lw_idle_min = 4, lw_passes = 4;
+  int32_t learn_order = 1;   // warp-queue kernel: claim order learned from the first frame of the same prepared scene and geometry
+                             // (long-path tiles first); 0 = off
+  int32_t long_path = 4;     // ... a tile is "long" when one of its paths had at least this many segments (negative: four classes
+                             // with thresholds 8x / 3x / 1x |long_path|)
   int32_t heavy_first = 0;   // pull long-path tiles to the front of the claim order: 0 off (default: the probe pass costs more than the tail it saves on one GPU, see profiles/), 1/2/4 = probe pixels per tile, -1 = on when spp > 1
   int32_t probe_segments = 8;
   std::string cache_file;
@@ -115,6 +119,19 @@ struct futhark_opaque_prepared_scene {
   // only after both (release_scene_block)
   mutable cudaEvent_t last_use[2] = {nullptr, nullptr};
   mutable bool used[2] = {false, false};
+  // Learned claim order (api_render.cu, do_render): the first frame of a given geometry records the longest path of every
+  // tile, later frames of the same prepared scene and geometry claim the long-path tiles first.  The scene and the camera
+  // are fixed in a prepared scene, so a tile's paths are the same in every frame (main.c renders the same frame `runs` times).
+  struct OrderCache {
+    int64_t h = 0, w = 0;
+    int32_t spp = 0, rank = 0, world = 0;
+    int64_t tiles = 0;
+    uint32_t *cost = nullptr;   // device [tiles]
+    int32_t *order = nullptr;   // device [tiles]
+    int state = 0;              // 0 empty, 1 order enqueued (the sort follows the recording frame on that frame's lane)
+    cudaEvent_t ready = nullptr; // recorded behind the sort: frames on the other lane wait for it before they read `order`
+  };
+  mutable OrderCache order_cache;
 };
 
 struct futhark_i32_2d {

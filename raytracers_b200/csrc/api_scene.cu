@@ -50,14 +50,19 @@ namespace rayb200_api {
 // the context's reclaim stream behind the last use on both lanes; the context's stream itself is never made to wait.
 int release_scene_block(futhark_context *ctx, futhark_opaque_prepared_scene *p) {
   if (!p->dev.block) return 0;
+  cudaStream_t where = ctx->stream;   // only ever used in the context's stream order: free there
   if (p->used[1]) {
     if (!ctx->reclaim) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->reclaim, cudaStreamNonBlocking));
     for (int l = 0; l < 2; l++)
       if (p->used[l]) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->reclaim, p->last_use[l], 0));
-    CUDA_TRY(ctx, cudaFreeAsync(p->dev.block, ctx->reclaim));
-  } else {
-    CUDA_TRY(ctx, cudaFreeAsync(p->dev.block, ctx->stream));  // only ever used in the context's stream order
+    where = ctx->reclaim;
   }
+  CUDA_TRY(ctx, cudaFreeAsync(p->dev.block, where));
+  // the learned claim order goes with the build (it may be a different scene next time): the next frame records again;
+  // its table is read by the same frames as the scene, so it is freed behind them too
+  if (p->order_cache.cost) CUDA_TRY(ctx, cudaFreeAsync(p->order_cache.cost, where));
+  if (p->order_cache.ready) cudaEventDestroy(p->order_cache.ready);
+  p->order_cache = futhark_opaque_prepared_scene::OrderCache();
   p->dev = DeviceBvh();
   p->used[0] = p->used[1] = false;
   return 0;
@@ -68,6 +73,7 @@ void free_prepared_device(futhark_context *ctx, futhark_opaque_prepared_scene *p
   release_scene_block(ctx, p);
   for (int l = 0; l < 2; l++)
     if (p->last_use[l]) { cudaEventDestroy(p->last_use[l]); p->last_use[l] = nullptr; }
+
   if (p->pinned) {
     if (ctx->pinned_cache.size() < 4) ctx->pinned_cache.push_back({p->pinned, p->pinned_bytes, p->pinned_event});
     else { cudaEventSynchronize(p->pinned_event); cudaEventDestroy(p->pinned_event); cudaFreeHost(p->pinned); }

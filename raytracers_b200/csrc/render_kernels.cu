@@ -76,6 +76,24 @@ __global__ void __launch_bounds__(256) tile_probe_kernel(const __grid_constant__
   }
 }
 
+// Learned claim order: the probe replaced by what the previous frame of the same scene measured (the longest path of every
+// tile, recorded by finish_path).  Tiles with a long path keep their place in the permuted sequence but move in front of
+// all others, so the 50-bounce paths that end a frame are claimed in its first few percent.
+__global__ void __launch_bounds__(256) tile_cost_keys_kernel(const __grid_constant__ RenderParams P, const uint32_t *__restrict__ cost,
+                                                             const int long_path, uint32_t *__restrict__ keys, int32_t *__restrict__ ids) {
+  const long long lt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lt >= P.local_tiles) return;
+  const long long chunk = lt >> 6;
+  const uint32_t pos = (uint32_t)((chunk * P.chunk_stride_inv) % P.n_chunks) << 6 | (uint32_t)(lt & 63);
+  // long_path > 0: two classes (>= long_path first); long_path < 0: four classes with thresholds 8x / 3x / 1x |long_path|
+  const uint32_t c = cost[lt];
+  uint32_t cls;
+  if (long_path > 0) cls = c >= (uint32_t)long_path ? 0u : 3u;
+  else { const uint32_t lp = (uint32_t)(-long_path); cls = c >= 8u * lp ? 0u : (c >= 3u * lp ? 1u : (c >= lp ? 2u : 3u)); }
+  keys[lt] = (cls << 29) | pos;
+  ids[lt] = (int32_t)lt;
+}
+
 // ====================================================================================== K3: warp work-queue
 // Dense traversal.  K1/K2 bind a lane to a ray for a whole segment, so a warp's SIMT efficiency is
 // mean/max of its lanes' traversal lengths (ncu: 6.5 of 32 lanes active on rgbbox).  The reference's
@@ -155,7 +173,9 @@ __global__ void __launch_bounds__(kWqMaxThreads, 1) render_warpqueue_kernel(cons
   if (kSpread) cbuf = P.sample_buf + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * kWqRing * (size_t)spp;
 
   // A path in `slot` has ended with `colour`.
-  auto finish_path = [&](const int slot, const V3 colour) {
+  auto finish_path = [&](const int slot, const V3 colour, const int segs) {
+    // learned claim order (recording frame only): the longest path of the tile, sample 0 of its 32 pixels is evidence enough
+    if (P.tile_cost && (__float_as_int(p_sum[slot].w) & 0xffff) == 0) atomicMax(P.tile_cost + (p_item[slot] >> 5), (unsigned)segs);
     if (kSpread) {
       const int ms = __float_as_int(p_sum[slot].w);
       __stcg(cbuf + (size_t)(ms >> 16) * spp + (ms & 0xffff), make_float4(colour.x, colour.y, colour.z, 0.0f));
@@ -322,7 +342,7 @@ __global__ void __launch_bounds__(kWqMaxThreads, 1) render_warpqueue_kernel(cons
             V3 light = v3(pl.x, pl.y, pl.z), colour;
             int depth = __float_as_int(pl.w);
             shade_segment(sc, P, r, q.a, -1, 0.0f, light, depth, colour);
-            finish_path(slot, colour);
+            finish_path(slot, colour, depth + 1);
           }
         }
         const unsigned m = __ballot_sync(kFullMask, go);
@@ -546,7 +566,7 @@ __global__ void __launch_bounds__(kWqMaxThreads, 1) render_warpqueue_kernel(cons
         ray_d[slot] = make_float4(r.d.x, r.d.y, r.d.z, 0.0f);
         p_light[slot] = make_float4(light.x, light.y, light.z, __int_as_float(depth));
       } else {
-        finish_path(slot, colour);
+        finish_path(slot, colour, depth + 1);
       }
     }
     __syncwarp();
@@ -648,6 +668,22 @@ cudaError_t launch_render(const RenderParams &p, const LaunchConfig &lc, const W
   return e;
 }
 
+// Loads (and opts in to shared memory) the variants the default plan uses - K = 1 / 2, samples spread or not, and the three
+// staging cases: whole scene staged, tree partly staged with / without the packet walk - so that the first timed frame of
+// main.c does not pay CUDA's lazy function loading (measured: +10 ms on the first frame, +1 ms on main.c's 10-run
+// average).  12 of the 32 instantiations, ~70 ms once per process instead of ~300 ms for all kernels of all builds.
+cudaError_t preload_default_kernels(int max_dynamic_smem) {
+  cudaError_t e = cudaSuccess;
+#define RAYB200_PRE(KK, SP, PK, A, S) \
+  if (e == cudaSuccess) e = opt_in_dynamic_smem<render_warpqueue_kernel<KK, SP, PK, A, S>>(max_dynamic_smem)
+#define RAYB200_PRE3(KK, SP) \
+  RAYB200_PRE(KK, SP, false, true, true); RAYB200_PRE(KK, SP, true, false, false); RAYB200_PRE(KK, SP, false, false, false)
+  RAYB200_PRE3(1, false); RAYB200_PRE3(1, true); RAYB200_PRE3(2, false); RAYB200_PRE3(2, true);
+#undef RAYB200_PRE3
+#undef RAYB200_PRE
+  return e;
+}
+
 size_t tile_order_sort_bytes(int64_t local_tiles) {
   size_t bytes = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const int32_t *)nullptr,
@@ -662,6 +698,14 @@ void launch_tile_order(const RenderParams &p, const TileOrderBuffers &b, cudaStr
   cub::DeviceRadixSort::SortPairs(b.sort_tmp, bytes, b.keys, b.keys_sorted, b.ids, b.order, (int)p.local_tiles, 0,
                                   tile_order_key_bits(p.n_chunks), stream);
   if (launches) *launches += 2;  // the cub sort is counted as one
+}
+
+void launch_tile_order_from_cost(const RenderParams &p, const uint32_t *cost, int32_t long_path, const TileOrderBuffers &b,
+                                 cudaStream_t stream, int64_t *launches) {
+  tile_cost_keys_kernel<<<(unsigned)((p.local_tiles + 255) / 256), 256, 0, stream>>>(p, cost, long_path, b.keys, b.ids);
+  size_t bytes = b.sort_tmp_bytes;
+  cub::DeviceRadixSort::SortPairs(b.sort_tmp, bytes, b.keys, b.keys_sorted, b.ids, b.order, (int)p.local_tiles, 0, 32, stream);
+  if (launches) *launches += 2;
 }
 
 void launch_flag_wait(uint32_t *flag, uint32_t value, long long timeout_ns, unsigned long long *timeouts, cudaStream_t stream) {

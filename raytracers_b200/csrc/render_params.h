@@ -42,6 +42,9 @@ struct RenderParams {
   const int32_t *tile_order;
   int32_t chunk_stride_inv;  // chunk_stride * chunk_stride_inv = 1 (mod n_chunks): position of a tile chunk in the claim sequence
   int32_t probes_per_tile, probe_segments;
+  // learned claim order: when non-NULL (warp-queue kernel) every finished path records max(segments) of its 8x4 tile here;
+  // the next frame of the same prepared scene and geometry claims the tiles with long paths first (api_render.cu)
+  uint32_t *tile_cost;
   float4 *sample_buf;    // warp-queue kernel, spp > 1: [CTAs][warps][kWqRing][spp] finished-sample colours (else NULL)
   // persistent-threads work cursor ([0]; [1] counts the warps that have left the kernel when frame_flag is set) and
   // optional work counters
@@ -101,6 +104,7 @@ cudaError_t launch_lanewalk(const RenderParams &p, const LaunchConfig &lc, cudaS
 cudaError_t launch_alt_kernel(const RenderParams &p, const LaunchConfig &lc, const WavefrontBuffers *wf, cudaStream_t stream,
                               int64_t *launches);
 bool alt_kernels_built();
+cudaError_t preload_default_kernels(int max_dynamic_smem);  // render_kernels.cu: the variants of the default plan
 // Probe pass + sort that produce RenderParams::tile_order (see render_kernels.cu).  All buffers are device memory.
 struct TileOrderBuffers {
   uint32_t *keys, *keys_sorted;   // [local_tiles]
@@ -115,6 +119,10 @@ inline int tile_order_key_bits(int32_t n_chunks) {  // keys are positions < n_ch
   return bits;
 }
 void launch_tile_order(const RenderParams &p, const TileOrderBuffers &b, cudaStream_t stream, int64_t *launches);
+// The same order table from a recorded frame: tiles whose longest path had >= long_path segments first, both groups in
+// the permuted claim sequence (cost = RenderParams::tile_cost of the recorded frame)
+void launch_tile_order_from_cost(const RenderParams &p, const uint32_t *cost, int32_t long_path, const TileOrderBuffers &b,
+                                 cudaStream_t stream, int64_t *launches);
 // peer-frame flags (render_kernels.cu): 1-thread kernels on `stream`
 void launch_flag_wait(uint32_t *flag, uint32_t value, long long timeout_ns, unsigned long long *timeouts, cudaStream_t stream);
 void launch_flag_set(uint32_t *flag, uint32_t value, cudaStream_t stream);

@@ -409,6 +409,50 @@ def test_pipelined_submission_with_scene_reupload(R, oracle, kernel):
         assert_same(out, want[("rgbbox", 4)], f"after pipeline {kernel}")
 
 
+
+@pytest.mark.parametrize("long_path", [2, 12, 60])
+def test_learned_claim_order_is_invisible(R, oracle, golden, long_path):
+    """The first frame of a prepared scene on the context's stream records the longest path per tile, later frames claim
+    the long-path tiles first (RAY_LEARN_ORDER / RAY_LONG_PATH): only WHEN a tile is rendered may change.  Reference PNGs
+    (three frames each: recording, learned, learned), spp > 1 on partial tiles with the float framebuffer, a sharded
+    row-major frame, a size change (new recording) and a scene re-upload (cache dropped) must all stay bit-identical."""
+    import torch
+    for name in ("rgbbox_500", "irreg_500"):
+        want, _ = golden[name]
+        with R.Context(learn_order=1, long_path=long_path) as ctx:
+            pr = ctx.prepare_scene(500, 500, ctx.scene(name.split("_")[0]))
+            for rep in range(3):
+                img = ctx.render(500, 500, pr)
+                ctx.sync()
+                assert_same(img.values(), want, f"learned order {name} long_path={long_path} frame {rep}")
+                img.free()
+    h, w, spp = 135, 203, 3
+    want, want_rgb, _ = oracle.Scene.rgbbox().prepare(h, w).render(h, w, spp=spp, want_rgb=True)
+    w2, _, _ = oracle.Scene.rgbbox().prepare(h, w).render(64, 96)
+    with R.Context(learn_order=1, long_path=long_path) as ctx:
+        pr = ctx.prepare_scene(h, w, ctx.rgbbox())
+        for rep in range(3):
+            pix, rgb = ctx.render_host(h, w, pr, spp=spp, want_rgb=True)
+            assert_same(pix, want, f"learned order spp {spp} frame {rep}")
+            np.testing.assert_array_equal(rgb.view(np.uint32), want_rgb.view(np.uint32))
+        assert_same(ctx.render_host(64, 96, pr), w2, "other size: records again")
+        assert_same(ctx.render_host(64, 96, pr), w2, "other size: learned")
+        pr.reupload()
+        assert_same(ctx.render_host(h, w, pr, spp=spp), want, "after re-upload: records again")
+        assert_same(ctx.render_host(h, w, pr, spp=spp), want, "after re-upload: learned")
+        ctx.set_shard(1, 3)                       # a shard's row-major frame: only this rank's tiles, twice
+        for rep in range(2):
+            out = torch.zeros((h, w), dtype=torch.int32, device="cuda")
+            ctx.render_into(out.data_ptr(), h, w, pr, spp=spp)
+            ctx.sync()
+            got = out.cpu().numpy()
+            tiles_x = (w + 7) // 8
+            jj, ii = np.meshgrid(np.arange(h), np.arange(w), indexing="ij")
+            mine = ((jj // 4) * tiles_x + ii // 8) % 3 == 1
+            np.testing.assert_array_equal(got[mine], want[mine])
+            assert (got[~mine] == 0).all()
+
+
 def test_headline_config_64spp_kernels_agree(R):
     """BASELINE configs[1]/[2] (1000x1000, 64 spp): too slow for the CPU oracle inside a test, so the kernels
     (lane-bound K1, sample-spread K3, pixel-bound K3) are checked against each other bit-for-bit."""

@@ -1,0 +1,18 @@
+set -x
+timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/r2_test_all8.log 2>&1; echo "all tests rc=$?"; tail -n 4 gpurun_out/r2_test_all8.log
+timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/r2_bench4.json 2> gpurun_out/r2_bench4.err; echo "bench rc=$?"; tail -n 3 gpurun_out/r2_bench4.err
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/r2_bench4.json').read().strip().splitlines()[-1])
+print({k:d[k] for k in ('value','ms_per_step','strict_steps','e2e','frame_ms_1spp','gpu_launches')})
+print(d['roofline']['per_scene'], d['roofline']['frac'], d['roofline_issue']['frac'], d['roofline_issue']['per_scene'])
+print({k:(v['ms_per_frame'],v['roofline_frac'],v['issue_frac'],v['parity']['differing'] if v['parity'] else None) for k,v in d['extra'].items()})
+print(d['cpu_baseline']['value'], d['parity'])
+PY
+RAY_LEARN_ORDER=0 timeout 600 python bench.py --steps 20 --warmup 5 --no-extra --no-cpu-baseline > gpurun_out/r2_bench4_nolearn.json 2>/dev/null; python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/r2_bench4_nolearn.json').read().strip().splitlines()[-1])
+print('RAY_LEARN_ORDER=0', {k:d[k] for k in ('value','ms_per_step','strict_steps','e2e','frame_ms_1spp')})
+PY
+python tools/context_new_time.py raytracers_b200/_ab/libray_r1.so; python tools/context_new_time.py
+for s in rgbbox irreg; do ./examples/_built/main_ref -s $s -n 1000 -m 1000 2>&1 | tail -n 3; done
