@@ -10,13 +10,23 @@ per pixel (BASELINE.json configs[1] and configs[2], the configs its metric "Mray
 `objs_hit` call; the per-frame segment counts come from the library's counting kernel
 and equal the oracle's (tests/test_gpu_parity.py::test_work_counters_equal_reference_traversal).
 
-Prints ONE JSON line (rank 0).  `value` = segments of all frames of a step / device time (scene
-resident in HBM, CUDA events, max over ranks); `e2e` = the same through host buffers: H2D of the packed
-sphere records from pinned memory + LBVH build on the device + render + D2H of the frame into pinned memory, wall clock; `roofline` = the
-render kernel's algorithmic bytes (32 B x box tests + 16 B x sphere tests + 4 B x pixels, reference
-traversal counts) / its measured duration vs the measured HBM peak; `cpu_baseline` = the CPU oracle
-(a bit-exact port of the reference's Futhark program; the Futhark compiler is not available here) on a
-bounded sample of the same workload.
+Prints ONE JSON line (rank 0).
+`value` = segments of all frames of K steps / device time (scene resident in HBM, CUDA events on the launch stream, max over
+ranks).  Default protocol: the K steps are submitted back to back with pipelined submission (ray_b200_context_set_pipeline:
+frames alternate between two lanes across steps, so a frame's last 50-bounce paths are covered by the next frame's start), ONE
+event pair around all K steps, the per-step L2 flush inside it; `strict_steps` repeats the K steps in the round-1 protocol
+(every step one joined batch between its own event pair) for comparison, `--strict-steps` makes that the headline.
+`e2e` = the same through host buffers, wall clock with barrier + synchronize on both sides: per step H2D of every scene's packed
+sphere records from pinned memory + LBVH build on the device (every rank), the step's frames as one batch, and every frame's D2H
+into pinned host memory (rank 0) through the peer-frame ring (raytracers_b200.distributed.PeerFrameRenderer; at N > 1 the other
+ranks' kernels write their pixels straight into rank 0's frame over NVLink) - the delivered host frames are compared with the
+oracle in `parity`.  `--gather nccl` switches N > 1 to tile buffers + one ncclGather + de-tiling per frame.
+`roofline` = the render kernel's algorithmic bytes (32 B x box tests + 16 B x sphere tests + 4 B x pixels, reference traversal
+counts) / its measured duration vs the measured HBM peak - an accounting figure, the scene is shared-memory resident;
+`roofline_issue` = useful thread-instructions of the reference traversal / the chip's issue capacity - the bound that applies;
+`parity` / `extra.*.parity` = differing pixels between the GPU frames and the oracle's row samples of the SAME frames (timed
+workload and the other BASELINE configs); `cpu_baseline` = the CPU oracle (a bit-exact port of the reference's Futhark program;
+the Futhark compiler is not available here) on a bounded sample of the same workload.
 
 --impl reference times that same CPU port on all host cores (no GPU work), one bounded sample per step.
 """
@@ -556,7 +566,7 @@ def run_ours(args):
                 ctx.render_into(fr.data_ptr(), hh, ww, pr, spp=spp)
                 torch.cuda.synchronize()
                 ms.append(ctx.last_render_ms())
-            m = sorted(ms)[len(ms) // 2]
+            m = sorted(ms)[(len(ms) - 1) // 2]   # (lower) median; the first frame of a scene also records the learned claim order
             gb = (32 * wk["box_tests"] + 16 * wk["leaf_tests"] + 4 * hh * ww) / 1e9
             par = None
             if not args.no_cpu_baseline:   # oracle rows (j - row_start) % row_step == 0 of this very frame
@@ -616,7 +626,7 @@ def run_ours(args):
                        "ray": "one ray segment = one objs_hit call (ray.fut:76-86)"},
             "strict_steps": strict, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_issue": issue_all,
             "parity": parity, "cpu_baseline": cpu,
-            "frame_ms_1spp": one_spp, "extra": extra, "shard_kernel_ms_per_rank": rank_kernel_ms,
+            "frame_ms_1spp": one_spp, "learned_claim_order": os.environ.get("RAY_LEARN_ORDER", "1") != "0", "extra": extra, "shard_kernel_ms_per_rank": rank_kernel_ms,
             "published_reference_1spp_ms": PUBLISHED_1SPP_MS,
         }
         print(json.dumps(line), flush=True)

@@ -90,6 +90,7 @@ struct futhark_context {
     TileOrderBuffers tile_order_plan{};
   } lanes[2];
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool plan_auto_k2 = false, suppress_auto_k2 = false;   // fill_params: the K = 2 plan was chosen automatically / must not be
   bool pipeline = false;                // ray_b200_context_set_pipeline: batches do not join lane 1 back
   uint32_t lane_seq = 0;                // pipelined submission: frames alternate lanes across calls
   cudaStream_t reclaim = nullptr;       // scene memory is freed here, ordered after its last use on either lane
@@ -156,7 +157,7 @@ void set_error(futhark_context *ctx, const char *fmt, ...);
   } while (0)
 
 inline bool bad_ctx(futhark_context *ctx) { return ctx == nullptr || !ctx->ok; }
-constexpr int kAutoK2Warps = 24, kAutoK2Ncap = 256;   // warp-queue kernel, wq_k = 0: the plan for scenes that fit shared memory whole
+constexpr int kAutoK2MinWarps = 20, kAutoK2Ncap = 256;   // warp-queue kernel, wq_k = 0: the plan for scenes that fit shared memory whole
 constexpr size_t kSpreadBudget = (size_t)1 << 30;  // cap on the finished-sample buffer of the sample-spreading kernels
 
 inline int64_t tiles_total(int64_t h, int64_t w) { return ((h + kTileH - 1) / kTileH) * ((w + kTileW - 1) / kTileW); }
@@ -184,7 +185,7 @@ int create_helper_contexts(futhark_context *ctx, const futhark_context_config *c
 int render_multi_device(futhark_context *ctx, futhark_i32_2d *img, int64_t h, int64_t w, int32_t spp, const futhark_opaque_prepared_scene *p);
 // api_scene.cu
 void free_prepared_device(futhark_context *ctx, futhark_opaque_prepared_scene *p);
-int release_scene_block(futhark_context *ctx, futhark_opaque_prepared_scene *p);
+int release_scene_block(futhark_context *ctx, futhark_opaque_prepared_scene *p, bool drop_order);
 int prepare_on_device(futhark_context *ctx, futhark_opaque_prepared_scene *p);
 int prepare_any(futhark_context *ctx, futhark_opaque_prepared_scene *p);
 

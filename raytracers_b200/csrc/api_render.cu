@@ -112,19 +112,29 @@ int fill_params(futhark_context *ctx, const futhark_opaque_prepared_scene *p, in
   if (kern == RAY_B200_KERNEL_WARPQUEUE) {
     // one CTA per SM: as many warps as asked for (<= 32) while their queues leave >= 8 KB for staging;
     // deep trees need bigger node stacks, so they get fewer warps
-    // Rays in flight per warp (32 K) and node-queue cap.  wq_k = 0 (default): K = 2 with kAutoK2Warps warps and a
-    // kAutoK2Ncap-entry node queue when the WHOLE scene (tree + spheres) still fits next to those queues - a round of 64
-    // rays has relatively fewer partial batches at its end than a round of 32 (rgbbox 64 spp 38.08 -> 36.84 ms,
+    // Rays in flight per warp (32 K) and node-queue cap.  wq_k = 0 (default): K = 2 with a kAutoK2Ncap-entry node queue and
+    // as many warps (>= kAutoK2MinWarps) as still leave the WHOLE scene (tree + spheres) staged - a round of 64 rays has
+    // relatively fewer partial batches at its end than a round of 32 (rgbbox 64 spp 38.08 -> 36.84 ms with 24 warps,
+    // -> 36.07 with the 28 that fit since spread samples keep 4 instead of 16 bytes of per-slot sample state;
     // profiles/r2_sweep_k2.json) - and K = 1 with 32 warps otherwise (a scene that is only partly staged loses more from
     // the staging space the bigger slots take: irreg 13.5 -> 25+ ms).
     int k = ctx->cfg.wq_k == 2 ? 2 : 1;
     int ncap_cfg = ctx->cfg.wq_ncap, warps_cfg = ctx->cfg.wq_warps;
-    if (ctx->cfg.wq_k == 0) {
+    bool auto_k2 = false;
+    // samples will be spread if the finished-sample buffer fits the budget (do_render allocates it; a failed allocation
+    // there falls back to pixel-bound samples, whose bigger slots are checked again at launch)
+    const bool will_spread = spp > 1 && spp <= 65535 && ctx->cfg.wq_spread &&
+                             (size_t)ctx->sm_count * kWqMaxWarps * kWqRing * (size_t)spp * sizeof(float4) <= kSpreadBudget;
+    if (ctx->cfg.wq_k == 0 && !ctx->suppress_auto_k2) {
       const int64_t scene_bytes = 128 + (int64_t)(p->n - 1) * 64 + (int64_t)p->n * 16;
-      const int64_t q2 = (int64_t)kAutoK2Warps * (int64_t)wq_warp_bytes(2, wq_node_capacity(2, p->max_depth, kAutoK2Ncap), false);
-      if (q2 + scene_bytes + 512 + 128 <= (int64_t)ctx->max_smem_optin) {
+      const int64_t pw2 = (int64_t)wq_warp_bytes(2, wq_node_capacity(2, p->max_depth, kAutoK2Ncap), false, will_spread);
+      int64_t w2 = ((int64_t)ctx->max_smem_optin - scene_bytes - 512 - 128) / pw2;   // as many warps as still leave the scene whole
+      if (w2 > kWqMaxWarps) w2 = kWqMaxWarps;
+      w2 &= ~(int64_t)3;             // the same number of warps on each of the SM's four schedulers
+      if (w2 >= kAutoK2MinWarps) {   // 28 warps with spread samples (80-byte slots), 24 with pixel-bound ones, on rgbbox
         k = 2;
-        if (warps_cfg < 1) warps_cfg = kAutoK2Warps;
+        auto_k2 = true;
+        if (warps_cfg < 1) warps_cfg = (int)w2;
         if (ctx->cfg.wq_ncap == 512) ncap_cfg = kAutoK2Ncap;   // (512 = the configured default: not set by the caller)
       }
     }
@@ -132,12 +142,14 @@ int fill_params(futhark_context *ctx, const futhark_opaque_prepared_scene *p, in
     // AND the rays a warp holds are coherent: samples of one pixel (spp > 1) or primary rays of a dense frame.
     // Measured: irreg 64 spp -19 %, irreg 4000^2 1 spp -12 %; rgbbox (fully staged) +1..2 %; 1000^2 1 spp +5 %.
     // The plan is made twice: first assuming packets, to see whether the tree would be fully staged anyway.
-    int want_packet = ctx->cfg.wq_packet;
+    // (the K = 2 plan is only made for scenes that are staged whole, where packets never pay: without this the first
+    // attempt below would reserve the packet stacks, find the scene no longer fits next to them and switch packets ON)
+    int want_packet = (auto_k2 && ctx->cfg.wq_packet < 0) ? 0 : ctx->cfg.wq_packet;
     const bool coherent = spp > 1 || h * w >= ((int64_t)1 << 22);
     int64_t per_warp = 0, wq_w = 0;
     for (int attempt = 0; attempt < 2; attempt++) {
       const bool pk = want_packet != 0;
-      per_warp = (int64_t)wq_warp_bytes(k, wq_node_capacity(k, p->max_depth, ncap_cfg), pk);
+      per_warp = (int64_t)wq_warp_bytes(k, wq_node_capacity(k, p->max_depth, ncap_cfg), pk, will_spread);
       // 32 warps hide latency best, also for the 1 M-sphere tree (64 MB of nodes) once its staging area is capped so
       // that the SM keeps 32 KB of L1 (below; profiles/r2_sweep_stage_cap.json: 91.4 ms with 24 warps and everything
       // staged -> 77.5 ms with 32 warps and 2 KB staged)
@@ -156,6 +168,7 @@ int fill_params(futhark_context *ctx, const futhark_opaque_prepared_scene *p, in
     ctx->plan_wq_warps = (int32_t)wq_w;
     ctx->plan_wq_k = k;
     ctx->plan_wq_ncap = ncap_cfg;
+    ctx->plan_auto_k2 = auto_k2;
   }
   if (kern == RAY_B200_KERNEL_LANEWALK) {
     // one CTA per SM: lw_warps warps (32 unless told otherwise) x lw_slots path slots each (48 unless told otherwise,
@@ -192,6 +205,14 @@ int fill_params(futhark_context *ctx, const futhark_opaque_prepared_scene *p, in
   P.smem_nodes = (int32_t)std::min<int64_t>(P.n_inner, nodes_fit);
   const int64_t left = budget - (int64_t)P.smem_nodes * 64;
   P.smem_spheres = (P.smem_nodes == P.n_inner && left >= (int64_t)P.n_leaves * 16) ? P.n_leaves : 0;
+  if (kern == RAY_B200_KERNEL_WARPQUEUE && ctx->plan_auto_k2 && !(P.smem_nodes == P.n_inner && P.smem_spheres == P.n_leaves)) {
+    // belt and braces: the K = 2 plan is only worth anything when the scene is staged whole (a scene that just misses costs
+    // 2 x: rgbbox 36 -> 71 ms); if anything above left it short, plan again with K = 1
+    ctx->suppress_auto_k2 = true;
+    const int rc = fill_params(ctx, p, h, w, spp, rank, world, out_pix, out_rgb, tile_major, P);
+    ctx->suppress_auto_k2 = false;
+    return rc;
+  }
   return 0;
 }
 

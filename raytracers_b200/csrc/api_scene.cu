@@ -48,7 +48,7 @@ namespace rayb200_api {
 // Gives the scene's device block back to the stream-ordered pool.  Frames may still be reading it on either lane
 // (pipelined submission does not join the lanes): if the scene was ever rendered on the second lane, the free goes to
 // the context's reclaim stream behind the last use on both lanes; the context's stream itself is never made to wait.
-int release_scene_block(futhark_context *ctx, futhark_opaque_prepared_scene *p) {
+int release_scene_block(futhark_context *ctx, futhark_opaque_prepared_scene *p, bool drop_order) {
   if (!p->dev.block) return 0;
   cudaStream_t where = ctx->stream;   // only ever used in the context's stream order: free there
   if (p->used[1]) {
@@ -58,19 +58,22 @@ int release_scene_block(futhark_context *ctx, futhark_opaque_prepared_scene *p) 
     where = ctx->reclaim;
   }
   CUDA_TRY(ctx, cudaFreeAsync(p->dev.block, where));
-  // the learned claim order goes with the build (it may be a different scene next time): the next frame records again;
-  // its table is read by the same frames as the scene, so it is freed behind them too
-  if (p->order_cache.cost) CUDA_TRY(ctx, cudaFreeAsync(p->order_cache.cost, where));
-  if (p->order_cache.ready) cudaEventDestroy(p->order_cache.ready);
-  p->order_cache = futhark_opaque_prepared_scene::OrderCache();
+  // The learned claim order stays: a prepared scene's spheres and camera never change (ray_b200_prepared_reupload builds
+  // the same tree again), so what the recording frame measured remains true.  When the object itself goes
+  // (`drop_order`), its table is freed behind the same frames as the scene.
+  if (drop_order) {
+    if (p->order_cache.cost) CUDA_TRY(ctx, cudaFreeAsync(p->order_cache.cost, where));
+    if (p->order_cache.ready) cudaEventDestroy(p->order_cache.ready);
+    p->order_cache = futhark_opaque_prepared_scene::OrderCache();
+  }
   p->dev = DeviceBvh();
-  p->used[0] = p->used[1] = false;
+  if (drop_order) p->used[0] = p->used[1] = false;
   return 0;
 }
 
 void free_prepared_device(futhark_context *ctx, futhark_opaque_prepared_scene *p) {
   cudaSetDevice(ctx->cfg.device);
-  release_scene_block(ctx, p);
+  release_scene_block(ctx, p, true);
   for (int l = 0; l < 2; l++)
     if (p->last_use[l]) { cudaEventDestroy(p->last_use[l]); p->last_use[l] = nullptr; }
 
@@ -98,7 +101,7 @@ int prepare_on_device(futhark_context *ctx, futhark_opaque_prepared_scene *p) {
   CUDA_TRY(ctx, cudaEventRecord(p->pinned_event, ctx->stream));
   const double t1 = timing ? now_us() : 0.0;
   p->refit_sweeps = (int32_t)log2f((float)(int64_t)n) + 2;  // bvh.fut:47, host libm as in the reference's C backend
-  if (release_scene_block(ctx, p)) return 1;
+  if (release_scene_block(ctx, p, false)) return 1;
   CUDA_TRY(ctx, build_bvh_device(d_spheres, (int64_t)n, p->refit_sweeps, p->dev, ctx->d_build_result, ctx->stream, &ctx->launches));
   CUDA_TRY(ctx, cudaFreeAsync(d_spheres, ctx->stream));
   // the host needs the tree depth (stack sizing) and the root box (kernel parameter) before the first render
@@ -140,7 +143,7 @@ int prepare_on_host(futhark_context *ctx, futhark_opaque_prepared_scene *p) {
   memcpy(hostside.right, tree.right.data(), ni * 4);
   memcpy(hostside.parent, tree.parent.data(), ni * 4);
   memcpy(hostside.boxes, tree.boxes.data(), ni * 24);
-  if (release_scene_block(ctx, p)) return 1;
+  if (release_scene_block(ctx, p, false)) return 1;
   unsigned char *blk = nullptr;
   CUDA_TRY(ctx, cudaMallocAsync(&blk, total, ctx->stream));
   carve_device_bvh(blk, n, p->dev);

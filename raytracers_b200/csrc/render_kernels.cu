@@ -143,13 +143,15 @@ __global__ void __launch_bounds__(kWqMaxThreads, 1) render_warpqueue_kernel(cons
     lt_mask = (1u << lane) - 1u;
     gt_mask = lane == 31 ? 0u : ~((2u << lane) - 1u);
   }
-  unsigned char *wbase = smem_raw + ((staging_bytes(P) + 127) & ~(size_t)127) + (size_t)warp * wq_warp_bytes(K, ncap, kPacket);
+  unsigned char *wbase = smem_raw + ((staging_bytes(P) + 127) & ~(size_t)127) + (size_t)warp * wq_warp_bytes(K, ncap, kPacket, kSpread);
   float4 *ray_o = reinterpret_cast<float4 *>(wbase);   // {o.xyz, a = dot d d}
   float4 *ray_i = ray_o + R;                           // {1/d.xyz, 0}
   float4 *ray_d = ray_i + R;                           // {d.xyz, 0}
   float4 *p_light = ray_d + R;                         // {light.rgb, bits(depth)}   owner lane only
-  float4 *p_sum = p_light + R;                         // {sum.rgb, bits(sample)} / spread: w = bits(ring << 16 | sample)
-  uint32_t *best_t = reinterpret_cast<uint32_t *>(p_sum + R);  // bits(t) of the closest accepted hit (kItemNoHit = none) ...
+  float4 *p_sum = p_light + R;                         // pixel-bound samples: {sum.rgb, bits(sample)}
+  int *p_ms = reinterpret_cast<int *>(p_light + R);    // spread samples: ring entry << 16 | sample (4 bytes per slot instead of 16)
+  uint32_t *best_t = kSpread ? reinterpret_cast<uint32_t *>(p_ms + R)   // bits(t) of the closest accepted hit (kItemNoHit = none) ...
+                             : reinterpret_cast<uint32_t *>(p_sum + R);
   uint32_t *best_l = best_t + R;                       // ... and its leaf, lowest index among equal t (fold_hit)
   int *p_item = reinterpret_cast<int *>(best_l + R);   // work item (pixel) of the slot, -1 = idle
   int *ring_item = p_item + R;                         // spread: pixel item of ring entry m
@@ -175,9 +177,10 @@ __global__ void __launch_bounds__(kWqMaxThreads, 1) render_warpqueue_kernel(cons
   // A path in `slot` has ended with `colour`.
   auto finish_path = [&](const int slot, const V3 colour, const int segs) {
     // learned claim order (recording frame only): the longest path of the tile, sample 0 of its 32 pixels is evidence enough
-    if (P.tile_cost && (__float_as_int(p_sum[slot].w) & 0xffff) == 0) atomicMax(P.tile_cost + (p_item[slot] >> 5), (unsigned)segs);
+    if (P.tile_cost && ((kSpread ? p_ms[slot] : __float_as_int(p_sum[slot].w)) & 0xffff) == 0)
+      atomicMax(P.tile_cost + (p_item[slot] >> 5), (unsigned)segs);
     if (kSpread) {
-      const int ms = __float_as_int(p_sum[slot].w);
+      const int ms = p_ms[slot];
       __stcg(cbuf + (size_t)(ms >> 16) * spp + (ms & 0xffff), make_float4(colour.x, colour.y, colour.z, 0.0f));
       atomicAdd(ring_done + (ms >> 16), 1);
       p_item[slot] = -1;
@@ -307,7 +310,7 @@ __global__ void __launch_bounds__(kWqMaxThreads, 1) render_warpqueue_kernel(cons
                 ray_o[slot] = make_float4(r.o.x, r.o.y, r.o.z, 0.0f);
                 ray_d[slot] = make_float4(r.d.x, r.d.y, r.d.z, 0.0f);
                 p_light[slot] = make_float4(1.0f, 1.0f, 1.0f, __int_as_float(0));
-                p_sum[slot] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float((m << 16) | s));
+                p_ms[slot] = (m << 16) | s;
               } else {
                 atomicAdd(ring_done + m, 1);  // padding pixel of a partial tile: nothing to trace
               }
@@ -633,7 +636,7 @@ cudaError_t launch_render(const RenderParams &p, const LaunchConfig &lc, const W
   const int wthreads = 32 * lc.wq_warps;
   const int ncap = wq_node_capacity(k, p.max_depth, lc.wq_ncap);
   const bool packet = lc.wq_packet > 0;
-  const size_t wsmem = ((staging_bytes(p) + 127) & ~(size_t)127) + (size_t)lc.wq_warps * wq_warp_bytes(k, ncap, packet);
+  const size_t wsmem = ((staging_bytes(p) + 127) & ~(size_t)127) + (size_t)lc.wq_warps * wq_warp_bytes(k, ncap, packet, p.sample_buf != nullptr);
   long long ctas = lc.sm_count;
   const bool spread = p.sample_buf != nullptr;
   // no more CTAs than there are rays to start at once: a slot takes one SAMPLE when samples are spread, one pixel

@@ -158,9 +158,11 @@ __host__ __device__ inline int wq_node_capacity(int k, int max_depth, int cap) {
   const int c = wq_node_capacity(k, max_depth);
   return cap > 0 && cap < c ? (cap < 256 ? 256 : cap) : c;
 }
-__host__ __device__ inline size_t wq_warp_bytes(int k, int ncap, bool packet) {
+// (a slot = 4 float4 {origin + a, 1/dir, dir, light + depth} + best t / leaf + item, and per-pixel sample state: a float4
+// {sum, sample} when a slot owns a pixel, 4 bytes {ring entry, sample} when samples are spread)
+__host__ __device__ inline size_t wq_warp_bytes(int k, int ncap, bool packet, bool spread) {
   const size_t r = 32 * (size_t)k;
-  return ((r * (16 * 5 + 8 + 4) + 2 * kWqRing * 4 + (packet ? 2 * kWqPacketStack * 4 : 0) + kWqLeafStack * 4 + (size_t)ncap * 4) + 127) & ~(size_t)127;
+  return ((r * (16 * 4 + (spread ? 4 : 16) + 8 + 4) + 2 * kWqRing * 4 + (packet ? 2 * kWqPacketStack * 4 : 0) + kWqLeafStack * 4 + (size_t)ncap * 4) + 127) & ~(size_t)127;
 }
 // stream-queue kernel (K4): per-warp bytes (5 float4 + best + item + pending per slot, done/free lists, ring, stacks)
 __host__ __device__ inline size_t sq_warp_bytes(int k, int ncap) {

@@ -415,7 +415,7 @@ def test_learned_claim_order_is_invisible(R, oracle, golden, long_path):
     """The first frame of a prepared scene on the context's stream records the longest path per tile, later frames claim
     the long-path tiles first (RAY_LEARN_ORDER / RAY_LONG_PATH): only WHEN a tile is rendered may change.  Reference PNGs
     (three frames each: recording, learned, learned), spp > 1 on partial tiles with the float framebuffer, a sharded
-    row-major frame, a size change (new recording) and a scene re-upload (cache dropped) must all stay bit-identical."""
+    row-major frame, a size change (new recording) and a scene re-upload (same spheres, order kept) must all stay bit-identical."""
     import torch
     for name in ("rgbbox_500", "irreg_500"):
         want, _ = golden[name]
@@ -438,8 +438,8 @@ def test_learned_claim_order_is_invisible(R, oracle, golden, long_path):
         assert_same(ctx.render_host(64, 96, pr), w2, "other size: records again")
         assert_same(ctx.render_host(64, 96, pr), w2, "other size: learned")
         pr.reupload()
-        assert_same(ctx.render_host(h, w, pr, spp=spp), want, "after re-upload: records again")
-        assert_same(ctx.render_host(h, w, pr, spp=spp), want, "after re-upload: learned")
+        assert_same(ctx.render_host(h, w, pr, spp=spp), want, "after re-upload (same spheres: the learned order is kept)")
+        assert_same(ctx.render_host(h, w, pr, spp=spp), want, "after re-upload, second frame")
         ctx.set_shard(1, 3)                       # a shard's row-major frame: only this rank's tiles, twice
         for rep in range(2):
             out = torch.zeros((h, w), dtype=torch.int32, device="cuda")
