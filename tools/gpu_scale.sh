@@ -1,3 +1,4 @@
+# Scaling run on one multi-GPU box: NGPU=2|4|8 gpurun --gpus $NGPU -- bash tools/gpu_scale.sh  (results -> gpurun_out/)
 set -x
 N=${NGPU:-8}
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/r2_scale_final_n${N}.json 2> gpurun_out/r2_scale_final_n${N}.err; echo "bench rc=$?"; grep -v "OMP_NUM\|^\*\*\*" gpurun_out/r2_scale_final_n${N}.err | tail -n 5
