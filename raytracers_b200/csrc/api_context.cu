@@ -40,7 +40,7 @@ int parse_kernel(const char *v, int dflt) {
   return atoi(v);
 }
 
-const char *kTuningNames[] = {"kernel", "spp", "blocks_per_sm", "smem_budget", "refill_min", "tail_from", "wq_warps", "wq_k", "wq_spread", "wq_packet", "wq_refill", "wq_ncap", "wf_sort", "learn_order", "long_path", "stage_cap", "lw_slots", "lw_warps", "lw_idle_min", "lw_passes", "permute", "heavy_first", "probe_segments", "host_build", "rank", "world", "gpus"};
+const char *kTuningNames[] = {"kernel", "spp", "blocks_per_sm", "smem_budget", "refill_min", "tail_from", "wq_warps", "wq_k", "wq_spread", "wq_packet", "wq_refill", "wq_ncap", "wq_low", "wf_sort", "learn_order", "long_path", "stage_cap", "lw_slots", "lw_warps", "lw_idle_min", "lw_passes", "permute", "heavy_first", "probe_segments", "host_build", "rank", "world", "gpus"};
 constexpr int kNumTuning = sizeof(kTuningNames) / sizeof(kTuningNames[0]);
 
 }  // namespace
@@ -75,6 +75,7 @@ int futhark_context_config_set_tuning_param(struct futhark_context_config *cfg, 
   else if (!strcmp(name, "wq_k")) cfg->wq_k = (int32_t)v;
   else if (!strcmp(name, "wq_spread")) cfg->wq_spread = (int32_t)v;
   else if (!strcmp(name, "wq_refill")) cfg->wq_refill = (int32_t)v;
+  else if (!strcmp(name, "wq_low")) cfg->wq_low = (int32_t)v;
   else if (!strcmp(name, "wq_packet")) cfg->wq_packet = (int32_t)v;  // (size_t)-1 = decide per scene
   else if (!strcmp(name, "wq_ncap")) cfg->wq_ncap = (int32_t)v;
   else if (!strcmp(name, "wf_sort")) cfg->wf_sort = (int32_t)v;
@@ -117,6 +118,7 @@ struct futhark_context *futhark_context_new(struct futhark_context_config *cfg) 
   ctx->cfg.wq_spread = env_int("RAY_WQ_SPREAD", ctx->cfg.wq_spread);
   ctx->cfg.wq_packet = env_int("RAY_WQ_PACKET", ctx->cfg.wq_packet);
   ctx->cfg.wq_refill = env_int("RAY_WQ_REFILL", ctx->cfg.wq_refill);
+  ctx->cfg.wq_low = env_int("RAY_WQ_LOW", ctx->cfg.wq_low);
   ctx->cfg.wq_ncap = env_int("RAY_WQ_NCAP", ctx->cfg.wq_ncap);
   ctx->cfg.stage_cap = env_int("RAY_STAGE_CAP", ctx->cfg.stage_cap);
   ctx->cfg.wf_sort = env_int("RAY_WF_SORT", ctx->cfg.wf_sort);

@@ -29,7 +29,7 @@ struct futhark_context_config {
   int32_t rank = 0, world = 1;
   int32_t gpus = 1;  // > 1: this ONE process drives that many devices (RAY_GPUS; the drop-in multi-GPU mode of main.c)
   int32_t blocks_per_sm = 4, smem_budget = 48 * 1024, refill_min = 8, tail_from = 8;
-  int32_t wq_warps = 0 /* 0 = per scene: 32, or 24 for trees far larger than the caches */, wq_k = 0 /* 0 = per scene: 2 when the whole scene fits shared memory next to 24 warps' queues, else 1 */, wq_spread = 1, wq_packet = -1, wq_refill = 1, wq_ncap = 512, permute = 1, host_build = 0;
+  int32_t wq_warps = 0 /* 0 = per scene: 32, or 24 for trees far larger than the caches */, wq_k = 0 /* 0 = per scene: 2 when the whole scene fits shared memory next to 24 warps' queues, else 1 */, wq_spread = 1, wq_packet = -1, wq_refill = 1, wq_ncap = 512, wq_low = 0 /* node queue: breadth-first below this many items; 0 = half the ring, -1 = plain LIFO */, permute = 1, host_build = 0;
   int32_t stage_cap = -1;    // warp-queue / lane-walk kernels: cap (bytes) on the shared memory used for staging the tree; what is not
                              // used stays L1 cache.  -1 = per scene: everything for trees the caches hold; for trees far larger, what
                              // keeps the kernel's shared memory under the 196 KB carve-out (32 KB of L1 left)

@@ -285,6 +285,7 @@ int do_render(futhark_context *ctx, RenderParams &P, int lane_id, bool timed, co
   lc.tail_from = ctx->cfg.tail_from;
   lc.wq_warps = ctx->plan_wq_warps > 0 ? ctx->plan_wq_warps : 1;
   lc.wq_k = ctx->plan_wq_k == 2 ? 2 : 1;
+  lc.wq_low = ctx->cfg.wq_low;
   lc.wq_refill = ctx->cfg.wq_refill < 1 ? 1 : (ctx->cfg.wq_refill > 32 ? 32 : ctx->cfg.wq_refill);
   lc.wq_packet = ctx->plan_wq_packet;
   lc.wq_ncap = lc.kernel == RAY_B200_KERNEL_WARPQUEUE ? ctx->plan_wq_ncap : ctx->cfg.wq_ncap;

@@ -121,8 +121,8 @@ __global__ void __launch_bounds__(256) tile_cost_keys_kernel(const __grid_consta
 // ORDER when its last sample lands, which keeps the result bit-identical to the sequential definition.
 
 template <int K, bool kSpread, bool kPacket, bool kAllNodes, bool kSpheres>
-__global__ void __launch_bounds__(kWqMaxThreads, 1) render_warpqueue_kernel(const __grid_constant__ RenderParams P, const int ncap,
-                                                                   const int packet_min, const int refill_min) {
+__global__ void __launch_bounds__(kWqMaxThreads, 1) render_warpqueue_kernel(const __grid_constant__ RenderParams P, const int ncap_arg,
+                                                                   const int packet_min, const int refill_min, const int nlow) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   if (P.warp_trace && threadIdx.x == 0) atomicMin(P.warp_trace, global_timer_ns());
   const float4 *s_nodes, *s_geom;
@@ -131,6 +131,16 @@ __global__ void __launch_bounds__(kWqMaxThreads, 1) render_warpqueue_kernel(cons
 
   constexpr int R = 32 * K;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // the node queue is a ring of the largest power of two that fits its allocation (the launcher hands out powers of two
+  // unless a caller asked for an odd capacity)
+  const int ncap = 1 << (31 - __clz(ncap_arg));
+  const unsigned nmask = (unsigned)ncap - 1u;
+  // Oldest-first node batches (see drain) need the ring; measured, they pay everywhere except where the packet walk meets
+  // spread samples (64 consecutive samples of a pixel in a warp: irreg 64 spp 13.5 ms with the ring against 12.8 without -
+  // 8 more instructions per batch buy 1.6 % - while 1-spp frames of the same scenes gain 2-6 %), so that combination
+  // keeps the plain stack: no index masks, newest first.
+  constexpr bool kDeque = !(kPacket && kSpread);
+  auto ring = [&](const int i) { return kDeque ? (int)((unsigned)i & nmask) : i; };
   // Lane masks.  At 64 registers the compiler does not keep them live across the batch bodies; re-reading %lanemask_lt/gt
   // is one instruction where re-deriving them from the thread index is four, but it also changes the register
   // allocation: measured A/B (profiles/r2_sweep_kernel_ab.json) the special registers win on the packet variants
@@ -143,7 +153,7 @@ __global__ void __launch_bounds__(kWqMaxThreads, 1) render_warpqueue_kernel(cons
     lt_mask = (1u << lane) - 1u;
     gt_mask = lane == 31 ? 0u : ~((2u << lane) - 1u);
   }
-  unsigned char *wbase = smem_raw + ((staging_bytes(P) + 127) & ~(size_t)127) + (size_t)warp * wq_warp_bytes(K, ncap, kPacket, kSpread);
+  unsigned char *wbase = smem_raw + ((staging_bytes(P) + 127) & ~(size_t)127) + (size_t)warp * wq_warp_bytes(K, ncap_arg, kPacket, kSpread);
   float4 *ray_o = reinterpret_cast<float4 *>(wbase);   // {o.xyz, a = dot d d}
   float4 *ray_i = ray_o + R;                           // {1/d.xyz, 0}
   float4 *ray_d = ray_i + R;                           // {d.xyz, 0}
@@ -169,7 +179,7 @@ __global__ void __launch_bounds__(kWqMaxThreads, 1) render_warpqueue_kernel(cons
   if (lane < kWqRing) ring_done[lane] = -1;
   __syncwarp();
   bool exhausted = false;
-  int ntop = 0, ltop = 0;                      // warp-uniform stack heights
+  int ntop = 0, nhead = 0, ltop = 0;           // warp-uniform: node queue [nhead, ntop) (ring; nhead = 0 outside drain), leaf stack height
   int open_seq = 0, disp_seq = 0, disp_s = 0;  // spread dispenser (warp-uniform): pixels opened / next sample to hand out
   float4 *cbuf = nullptr;                      // spread: [kWqRing][spp] finished-sample colours of this warp
   if (kSpread) cbuf = P.sample_buf + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * kWqRing * (size_t)spp;
@@ -207,31 +217,37 @@ __global__ void __launch_bounds__(kWqMaxThreads, 1) render_warpqueue_kernel(cons
   // spread: pixels whose last sample has landed are summed IN SAMPLE ORDER and written; frees the ring entry
   auto finalize_pixels = [&]() {
     __syncwarp();
-    if (lane < kWqRing && ring_done[lane] == spp) {
-      const int item = ring_item[lane];
-      int pi, pj;
-      if (item_pixel(P, item, pi, pj)) {
-        const float4 *c = cbuf + (size_t)lane * spp;
-        const float4 c0 = __ldcg(c);
-        V3 sum = v3(c0.x, c0.y, c0.z);
-        for (int s = 1; s < spp; s++) {
-          const float4 cs = __ldcg(c + s);
-          sum = vadd(sum, v3(cs.x, cs.y, cs.z));
-        }
-        write_pixel(P, item, pi, pj, sum);
-      } else if (P.tile_major) {
-        P.out_pix[item] = 0;
+    // four lanes per ring entry, one per colour channel: the in-order sum is a dependent chain of spp - 1 additions per
+    // channel, so the three channels run side by side (one lane doing all three cost 3.6 % of irreg's instructions)
+    const int m = lane >> 2, ch = lane & 3;
+    const bool ready = ring_done[m] == spp;
+    if (__any_sync(kFullMask, ready)) {
+      float sum = 0.0f;
+      if (ready && ch < 3) {
+        const float *c = reinterpret_cast<const float *>(cbuf + (size_t)m * spp) + ch;
+        sum = __ldcg(c);
+#pragma unroll 4
+        for (int s = 1; s < spp; s++) sum = sum + __ldcg(c + 4 * s);
       }
-      ring_done[lane] = -1;
+      const float g = __shfl_down_sync(kFullMask, sum, 1), b = __shfl_down_sync(kFullMask, sum, 2);
+      if (ready && ch == 0) {
+        const int item = ring_item[m];
+        int pi, pj;
+        if (item_pixel(P, item, pi, pj)) write_pixel(P, item, pi, pj, v3(sum, g, b));
+        else if (P.tile_major) P.out_pix[item] = 0;
+      }
+      __syncwarp();  // every lane of the entry has read ring_done before it is reset
+      if (ready && ch == 0) ring_done[m] = -1;
     }
     __syncwarp();
   };
 
   for (;;) {
     unsigned trav = 0;  // bit k: slot lane+32k has a traversal in flight this round
-    unsigned gomask[K];  // warp-uniform: lanes whose slot lane+32k starts a traversal this round
-#pragma unroll
-    for (int k = 0; k < K; k++) gomask[k] = 0u;
+    // warp-uniform: lanes whose slot lane+32k starts a traversal this round.  (The per-k loops below are NOT unrolled:
+    // ncu had the K = 2 kernel's instruction working set at 34 KB against a 32 KB instruction cache - 9 % of the fetches
+    // missed it and the GPC-level cache behind it ran at 94 % of its peak - and refill / set-up / shading were in it twice.)
+    unsigned gomask0 = 0u, gomask1 = 0u;
     for (int pass = 0; pass < 4; pass++) {
       // ---------------------------------------------------------------- hand work to idle slots
       if (kSpread) finalize_pixels();
@@ -251,7 +267,7 @@ __global__ void __launch_bounds__(kWqMaxThreads, 1) render_warpqueue_kernel(cons
           int base = 0;
           if (lane == 0) base = atomicAdd(P.work_cursor, cnt);
           base = __shfl_sync(kFullMask, base, 0);
-#pragma unroll
+#pragma unroll 1
           for (int k = 0; k < K; k++) {
             const int slot = lane + 32 * k;
             if (p_item[slot] < 0) {
@@ -293,7 +309,7 @@ __global__ void __launch_bounds__(kWqMaxThreads, 1) render_warpqueue_kernel(cons
           avail += spp;
         }
         const int give = cnt < avail ? cnt : avail;
-#pragma unroll
+#pragma unroll 1
         for (int k = 0; k < K; k++) {
           const int slot = lane + 32 * k;
           if (p_item[slot] < 0) {
@@ -323,7 +339,7 @@ __global__ void __launch_bounds__(kWqMaxThreads, 1) render_warpqueue_kernel(cons
       // -------------------------------------------------------------- set up this round's segments
       // Root box test by the owner lane; a root miss is shaded (sky) on the spot and the path ends,
       // so sky rays never occupy a traversal round.
-#pragma unroll
+#pragma unroll 1
       for (int k = 0; k < K; k++) {
         const int slot = lane + 32 * k;
         bool go = false;
@@ -350,7 +366,7 @@ __global__ void __launch_bounds__(kWqMaxThreads, 1) render_warpqueue_kernel(cons
         }
         const unsigned m = __ballot_sync(kFullMask, go);
         if (go) trav |= 1u << k;
-        gomask[k] |= m;  // the traversal of these rays starts at the root after the passes
+        if (k == 0) gomask0 |= m; else gomask1 |= m;  // the traversal of these rays starts at the root after the passes
       }
       // another pass only helps if some slot is idle and there is still work to hand out
       bool idle_left = false;
@@ -360,10 +376,7 @@ __global__ void __launch_bounds__(kWqMaxThreads, 1) render_warpqueue_kernel(cons
       if (!more || !__any_sync(kFullMask, idle_left)) break;
     }
     __syncwarp();
-    unsigned any_go = 0u;
-#pragma unroll
-    for (int k = 0; k < K; k++) any_go |= gomask[k];
-    if (any_go == 0u) {
+    if ((gomask0 | gomask1) == 0u) {
       bool any_active = false;
 #pragma unroll
       for (int k = 0; k < K; k++) any_active |= p_item[lane + 32 * k] >= 0;
@@ -378,11 +391,11 @@ __global__ void __launch_bounds__(kWqMaxThreads, 1) render_warpqueue_kernel(cons
 
     // ---------------------------------------------------------------- dense traversal of the round
     // Both batch bodies exist twice: a full-warp version (32 items, no lane predicate: the four push flags stay in
-    // predicate registers) used while the stacks are deep enough, and a partial version for the drain.
-    auto leaf_batch = [&](auto full_tag) {
+    // predicate registers) used while the queues are deep enough, and a partial one for the drain.
+    auto leaf_batch = [&](auto full_tag, const int n_part) {
       // closest_hit (ray.fut:78-81) for up to 32 (ray, sphere) pairs
       constexpr bool kFull = decltype(full_tag)::value;
-      const int n = kFull ? 32 : ltop;
+      const int n = kFull ? 32 : n_part;
       bool hit = false;
       uint32_t tb = 0;
       int slot = 0, li = 0;
@@ -402,15 +415,16 @@ __global__ void __launch_bounds__(kWqMaxThreads, 1) render_warpqueue_kernel(cons
       ltop -= n;
       fold_hit(best_t, best_l, slot, hit, tb, (uint32_t)li);
     };
-    auto node_batch = [&](auto full_tag, const int n_part) {
-      // one BVH2C node step (both children's boxes) for up to 32 (ray, node) pairs
+    auto node_batch = [&](auto full_tag, const bool bottom, const int n_part) {
+      // one BVH2C node step (both children's boxes) for up to 32 (ray, node) pairs, taken from the top of the queue
+      // (newest = deepest first) or, `bottom` (warp-uniform), from its bottom (oldest = shallowest first)
       constexpr bool kFull = decltype(full_tag)::value;
       const int n = kFull ? 32 : n_part;
       bool pl_node = false, pr_node = false, pl_leaf = false, pr_leaf = false;
       uint32_t tag = 0;
       int lptr = 0, rptr = 0;
       if (kFull || lane < n) {
-        const uint32_t it = nstk[ntop - 1 - lane];
+        const uint32_t it = nstk[ring(kDeque && bottom ? nhead + lane : ntop + ~lane)];
         tag = it & ~kIndexMask;
         const int slot = (int)(it >> kSlotShift), cur = (int)(it & kIndexMask);
         const float4 ro = ray_o[slot], ri = ray_i[slot];
@@ -430,14 +444,14 @@ __global__ void __launch_bounds__(kWqMaxThreads, 1) render_warpqueue_kernel(cons
         pl_node = hl && !pl_leaf;
         pr_node = hr && !pr_leaf;
       }
-      __syncwarp();  // all pops have been read before anything is pushed over them
-      ntop -= n;
+      __syncwarp();  // top pops: all of them have been read before anything is pushed over them
+      if (kDeque && bottom) nhead += n; else ntop -= n;
       const unsigned bl = __ballot_sync(kFullMask, pl_node), br = __ballot_sync(kFullMask, pr_node);
       const unsigned cl = __ballot_sync(kFullMask, pl_leaf), cr = __ballot_sync(kFullMask, pr_leaf);
       // reverse lane order: lane 0 popped the top (deepest) item, its children go back on top
       const int nb = ntop + __popc(bl & gt_mask) + __popc(br & gt_mask);
-      if (pr_node) nstk[nb] = tag | (uint32_t)rptr;
-      if (pl_node) nstk[nb + (pr_node ? 1 : 0)] = tag | (uint32_t)lptr;
+      if (pr_node) nstk[ring(nb)] = tag | (uint32_t)rptr;
+      if (pl_node) nstk[ring(nb + (pr_node ? 1 : 0))] = tag | (uint32_t)lptr;
       ntop += __popc(bl) + __popc(br);
       const int lb = ltop + __popc(cl & lt_mask) + __popc(cr & lt_mask);
       if (pl_leaf) lstk[lb] = tag | (uint32_t)(~lptr);
@@ -446,22 +460,33 @@ __global__ void __launch_bounds__(kWqMaxThreads, 1) render_warpqueue_kernel(cons
     };
     using full_t = std::integral_constant<bool, true>;
     using part_t = std::integral_constant<bool, false>;
-    // Runs the item queues dry.  Without packet spills the depth-sorted LIFO never exceeds the proved bound; with
-    // spills (arbitrary depths) a guard keeps it safe for ANY content: once fewer than 96 entries are free, items are
-    // taken one at a time, a plain DFS that can add at most (tree depth) < 64 entries before it shrinks again.
+    // Runs the item queues dry.  Order is free (the fold is a min), so it is chosen for full batches: while the node
+    // queue is short (<= nlow items) batches take its OLDEST items, which widens the frontier breadth-first and leaves only
+    // deep items (short subtrees) for the end of the round; above nlow they take the newest (depth-first), which bounds
+    // the queue.  With top-only popping the last items of a round were the root-level items at the bottom of the stack:
+    // ncu had 27.7 of 32 lanes active in the box tests (rgbbox, 64 rays per warp), ~10 partial batches per round; the
+    // scheduling simulation of the same rounds gives 0.87 -> 0.98 lane use and 11 % fewer node batches.
+    // Overflow guard for ANY content: once fewer than 96 entries are free, items are taken one at a time from the top,
+    // a plain DFS that can add at most (tree depth) < 64 entries before it shrinks again.
     auto drain = [&]() {
       __syncwarp();
       const int nroom = ncap - 96;
       for (;;) {
         // the common case first and alone in its loop: full node batches while nothing else is due (ncu: the general
-        // dispatch below cost ~12 instructions per batch, 10 % of the kernel's instructions)
-        while (ntop >= 32 && ntop <= nroom && ltop < 32) { node_batch(full_t{}, 32); __syncwarp(); }
-        if (ltop >= 32) leaf_batch(full_t{});
-        else if (ntop > 0) node_batch(part_t{}, ntop > nroom ? 1 : (ntop < 32 ? ntop : 32));
-        else if (ltop > 0) leaf_batch(part_t{});
+        // dispatch below cost ~12 instructions per batch, 10 % of the kernel's instructions).  One copy of the batch
+        // body for both pop directions.
+        while ((unsigned)(ntop - nhead - 32) <= (unsigned)(nroom - 32) && ltop < 32) {
+          node_batch(full_t{}, kDeque && ntop - nhead <= nlow, 32);
+          __syncwarp();
+        }
+        const int cnt = ntop - nhead;
+        if (ltop >= 32) leaf_batch(full_t{}, 32);
+        else if (cnt > 0) node_batch(part_t{}, false, cnt > nroom ? 1 : (cnt < 32 ? cnt : 32));
+        else if (ltop > 0) leaf_batch(part_t{}, ltop);
         else break;
         __syncwarp();
       }
+      ntop = nhead = 0;  // empty: outside the drain the queue is a plain array again
     };
     // Packet walk.  Near the root almost every ray of a warp visits the same nodes, so those node steps are done the
     // cheap way: ONE (node, lane mask) pair for the whole warp, the node fetched once (same address in every lane =
@@ -538,20 +563,21 @@ __global__ void __launch_bounds__(kWqMaxThreads, 1) render_warpqueue_kernel(cons
     };
 #pragma unroll
     for (int k = 0; k < K; k++) {
+      const unsigned gm = k == 0 ? gomask0 : gomask1;
       if (kPacket && packet_min > 0) {
         if constexpr (kPacket) {
-          if (gomask[k]) packet_walk(k, gomask[k]);
+          if (gm) packet_walk(k, gm);
         }
       } else {
-        const bool go = (gomask[k] >> lane) & 1u;
-        if (go) nstk[ntop + __popc(gomask[k] & lt_mask)] = (uint32_t)(lane + 32 * k) << kSlotShift;  // (slot, root node 0)
-        ntop += __popc(gomask[k]);
+        const bool go = (gm >> lane) & 1u;
+        if (go) nstk[ntop + __popc(gm & lt_mask)] = (uint32_t)(lane + 32 * k) << kSlotShift;  // (slot, root node 0)
+        ntop += __popc(gm);
       }
     }
     drain();
 
     // ---------------------------------------------------------------- shade: owner lanes finish the segment
-#pragma unroll
+#pragma unroll 1
     for (int k = 0; k < K; k++) {
       if (!((trav >> k) & 1u)) continue;
       const int slot = lane + 32 * k;
@@ -636,6 +662,9 @@ cudaError_t launch_render(const RenderParams &p, const LaunchConfig &lc, const W
   const int wthreads = 32 * lc.wq_warps;
   const int ncap = wq_node_capacity(k, p.max_depth, lc.wq_ncap);
   const bool packet = lc.wq_packet > 0;
+  // breadth-first below this many queued node items (0 = half the ring, < 0 = never: plain LIFO)
+  const int nring = 1 << (31 - __builtin_clz((unsigned)ncap));
+  const int nlow = lc.wq_low < 0 ? 0 : (lc.wq_low == 0 ? nring / 2 : (lc.wq_low > nring - 96 ? nring - 96 : lc.wq_low));
   const size_t wsmem = ((staging_bytes(p) + 127) & ~(size_t)127) + (size_t)lc.wq_warps * wq_warp_bytes(k, ncap, packet, p.sample_buf != nullptr);
   long long ctas = lc.sm_count;
   const bool spread = p.sample_buf != nullptr;
@@ -649,7 +678,7 @@ cudaError_t launch_render(const RenderParams &p, const LaunchConfig &lc, const W
   do {                                                                                                                      \
     e = opt_in_dynamic_smem<render_warpqueue_kernel<KK, SP, PK, A, S>>(lc.max_dynamic_smem);                                \
     if (e == cudaSuccess)                                                                                                   \
-      render_warpqueue_kernel<KK, SP, PK, A, S><<<(unsigned)ctas, wthreads, wsmem, stream>>>(p, ncap, lc.wq_packet, lc.wq_refill); \
+      render_warpqueue_kernel<KK, SP, PK, A, S><<<(unsigned)ctas, wthreads, wsmem, stream>>>(p, ncap, lc.wq_packet, lc.wq_refill, nlow); \
   } while (0)
 #define RAYB200_WQ2(KK, SP, PK)                                                           \
   do {                                                                                    \

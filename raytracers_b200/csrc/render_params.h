@@ -88,6 +88,7 @@ struct LaunchConfig {
   int wq_warps;        // warp-queue kernel: warps per CTA (one CTA per SM)
   int wq_k;            // warp-queue kernel: rays in flight per warp = 32 * wq_k (1 or 2)
   int wq_refill;       // warp-queue kernel, spread mode: hand out samples when at least this many slots are idle
+  int wq_low;          // warp-queue kernel: node batches take the OLDEST queued items while at most this many are queued (0 = half the ring, < 0 = never)
   int wq_packet;       // warp-queue kernel: node steps with at least this many lanes are done packet-style (0 = never)
   int wq_ncap;         // warp-queue kernel: cap on the node-queue capacity (0 = the proved bound, at most 1024)
   int lw_slots;        // lane-walk kernel: path slots per warp (32 lanes walk, the rest wait for / come from shading)
