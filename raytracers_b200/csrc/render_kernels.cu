@@ -146,7 +146,11 @@ __global__ void __launch_bounds__(kWqMaxThreads, 1) render_warpqueue_kernel(cons
   // allocation: measured A/B (profiles/r2_sweep_kernel_ab.json) the special registers win on the packet variants
   // (irreg 64 spp 13.88 -> 13.49 ms, 1 M spheres 77.6 -> 76.4) and lose on the fully staged one (rgbbox 38.05 -> 38.64).
   unsigned lt_mask, gt_mask;
+#ifdef RAYB200_LANEMASK_ALL
+  if constexpr (true) {
+#else
   if constexpr (kPacket) {
+#endif
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
     asm("mov.u32 %0, %%lanemask_gt;" : "=r"(gt_mask));
   } else {
@@ -447,16 +451,20 @@ __global__ void __launch_bounds__(kWqMaxThreads, 1) render_warpqueue_kernel(cons
       __syncwarp();  // top pops: all of them have been read before anything is pushed over them
       if (kDeque && bottom) nhead += n; else ntop -= n;
       const unsigned bl = __ballot_sync(kFullMask, pl_node), br = __ballot_sync(kFullMask, pr_node);
-      const unsigned cl = __ballot_sync(kFullMask, pl_leaf), cr = __ballot_sync(kFullMask, pr_leaf);
       // reverse lane order: lane 0 popped the top (deepest) item, its children go back on top
       const int nb = ntop + __popc(bl & gt_mask) + __popc(br & gt_mask);
       if (pr_node) nstk[ring(nb)] = tag | (uint32_t)rptr;
       if (pl_node) nstk[ring(nb + (pr_node ? 1 : 0))] = tag | (uint32_t)lptr;
       ntop += __popc(bl) + __popc(br);
-      const int lb = ltop + __popc(cl & lt_mask) + __popc(cr & lt_mask);
-      if (pl_leaf) lstk[lb] = tag | (uint32_t)(~lptr);
-      if (pr_leaf) lstk[lb + (pl_leaf ? 1 : 0)] = tag | (uint32_t)(~rptr);
-      ltop += __popc(cl) + __popc(cr);
+      // two batches in three have no leaf child at all (upper tree levels; the scheduling simulation of rgbbox counts
+      // 651 of 973): one vote instead of the two ballots, six popc and the stores
+      if (__any_sync(kFullMask, pl_leaf || pr_leaf)) {
+        const unsigned cl = __ballot_sync(kFullMask, pl_leaf), cr = __ballot_sync(kFullMask, pr_leaf);
+        const int lb = ltop + __popc(cl & lt_mask) + __popc(cr & lt_mask);
+        if (pl_leaf) lstk[lb] = tag | (uint32_t)(~lptr);
+        if (pr_leaf) lstk[lb + (pl_leaf ? 1 : 0)] = tag | (uint32_t)(~rptr);
+        ltop += __popc(cl) + __popc(cr);
+      }
     };
     using full_t = std::integral_constant<bool, true>;
     using part_t = std::integral_constant<bool, false>;
