@@ -22,7 +22,8 @@ def main():
     bad = 0
     h, w = 40, 72
     want = {(n, s): getattr(O.Scene, n)().prepare(h, w).render(h, w, spp=s)[0] for n in ("rgbbox", "irreg") for s in (1, 3)}
-    for kernel, tuning in (("warpqueue", {}), ("warpqueue", dict(wq_packet=8)), ("warpqueue", dict(wq_spread=0)), ("lanewalk", {})):
+    for kernel, tuning in (("warpqueue", {}), ("warpqueue", dict(wq_packet=8)), ("warpqueue", dict(wq_spread=0)), ("warpqueue", dict(wq_low=40, wq_k=1)),
+                           ("warpqueue", dict(wq_low=-1)), ("lanewalk", {})):
         with R.Context(kernel=kernel, **tuning) as ctx:
             prep = {n: ctx.prepare_scene(h, w, ctx.scene(n)) for n in ("rgbbox", "irreg")}
             for (n, s), wnt in want.items():
