@@ -30,6 +30,9 @@ WANT = {
     "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio": "stall_short_scoreboard",
     "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio": "stall_mio_throttle",
     "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio": "stall_wait",
+    "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio": "stall_no_instruction",
+    "sm__icc_request_hit_rate.pct": "icache_hit_pct",
+    "gcc__cache_requests_type_instruction.sum.pct_of_peak_sustained_elapsed": "gpc_icache_requests_pct_of_peak",
 }
 UNIT = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
 
@@ -71,6 +74,9 @@ def main():
     old = json.load(open(tp)) if os.path.exists(tp) else {}
     old.update({k: v for k, v in traffic.items() if k in ("rgbbox", "irreg")})
     old["random1M_2spp"] = traffic.get("random", old.get("random1M_2spp"))
+    old["source"] = ("ncu --set full, render_warpqueue_kernel as planned by default, 1000x1000 frames at 64 spp and the 1 M-sphere scene at 2 spp "
+                     "(tools/ncu_refresh.sh, profiles/r2_warpqueue_*_details.txt): dram__bytes_read.sum + dram__bytes_write.sum per launch. The scene is "
+                     "shared-memory / L2 resident; the frame (4 MB) is written once; the rest is spill of the L2-resident sample-colour buffer.")
     json.dump(old, open(tp, "w"), indent=1)
     print(json.dumps(out, indent=1))
     return 0
