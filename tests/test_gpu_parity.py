@@ -770,3 +770,31 @@ def test_device_lbvh_on_adversarial_scenes(R, oracle, mode):
             np.testing.assert_array_equal(got["boxes"].view(np.uint32), want["boxes"].view(np.uint32), err_msg=f"{mode} n={n} boxes")
             assert_same(ctx.render_host(16, 24, pr), want_pr.render(16, 24)[0], f"{mode} n={n} frame")
             pr.free()
+
+
+@pytest.mark.parametrize("wq_low", [-1, 32, 40, 100, 100000])
+def test_node_queue_pop_order_is_invisible(R, oracle, golden, wq_low):
+    """The node queue of the warp-queue kernel is a ring whose batches take the OLDEST items while at most `wq_low` are queued
+    and the newest above that (RAY_WQ_LOW; -1 = plain stack, values above the ring are clamped): the fold is a min, so the
+    order in which (ray, node) items are processed may not change a pixel.  Reference PNGs with 32 and 64 rays per warp, the
+    packet walk, spp > 1 (spread and pixel-bound samples) and the smallest ring with a deep tree (overflow guard)."""
+    for name in ("rgbbox_500", "irreg_500"):
+        want, _ = golden[name]
+        for tuning in (dict(), dict(wq_k=1), dict(wq_k=1, wq_packet=8), dict(wq_k=2, wq_ncap=256)):
+            with R.Context(kernel="warpqueue", wq_low=wq_low, **tuning) as ctx:
+                pr = ctx.prepare_scene(500, 500, ctx.scene(name.split("_")[0]))
+                assert_same(ctx.render_host(500, 500, pr), want, f"{name} wq_low={wq_low} {tuning}")
+    h, w = 61, 83
+    for name in ("rgbbox", "irreg"):
+        sc = getattr(oracle.Scene, name)()
+        for spp in (2, 5):
+            want, _, _ = sc.prepare(h, w).render(h, w, spp=spp)
+            for tuning in (dict(), dict(wq_spread=0), dict(wq_k=1, wq_packet=12)):
+                with R.Context(kernel="warpqueue", wq_low=wq_low, **tuning) as ctx:
+                    pr = ctx.prepare_scene(h, w, ctx.scene(name))
+                    assert_same(ctx.render_host(h, w, pr, spp=spp), want, f"{name} spp={spp} wq_low={wq_low} {tuning}")
+    n = 3000                                       # a deeper tree on the smallest (256-entry) ring: the overflow guard takes items one at a time
+    want, _, _ = oracle.Scene.random(n, seed=7).prepare(40, 56).render(40, 56)
+    with R.Context(kernel="warpqueue", wq_low=wq_low, wq_ncap=256) as ctx:
+        pr = ctx.prepare_scene(40, 56, ctx.scene("random", n=n, seed=7))
+        assert_same(ctx.render_host(40, 56, pr), want, f"random {n} wq_low={wq_low} ring 256")
