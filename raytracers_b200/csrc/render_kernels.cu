@@ -100,17 +100,21 @@ __global__ void __launch_bounds__(256) tile_cost_keys_kernel(const __grid_consta
 // fold is order-free and never prunes by the running closest t, so a segment's traversal is just a
 // SET of independent (ray, node) box-test items and (ray, leaf) sphere-test items.  K3 therefore
 // binds lanes to ITEMS, not rays: every warp keeps R = 32*K rays in flight, their traversal items on
-// a warp-private LIFO in shared memory, and each iteration pops 32 items — whatever rays they belong
+// a warp-private queue in shared memory, and each iteration takes 32 items — whatever rays they belong
 // to — so every lane does one node step (two box tests) or one sphere test.  Children are pushed back
-// with ballot/popc compaction; a sphere hit is folded into its ray's 64-bit (t, leaf index) word with
-// atomicMin, which is exactly the reference's "smallest t, lowest leaf index on ties".  When the
-// stacks run dry every ray of the round has its closest hit; the owner lanes shade, bounce, and idle
-// slots are refilled, and the next round starts.
+// with ballot/popc compaction; a sphere hit is folded into its ray's (t, leaf index) pair with two
+// 32-bit shared-memory atomicMin (fold_hit), which is exactly the reference's "smallest t, lowest leaf
+// index on ties".  When the queues run dry every ray of the round has its closest hit; the owner lanes
+// shade, bounce, and idle slots are refilled, and the next round starts.
 //
-// Stack bound: items are pushed in reverse lane order, which keeps the LIFO sorted by tree depth
-// (deepest on top); then at most 64 items of any depth are live at once (children of one 32-item
-// batch), so R + 64*(max_depth+1) entries always suffice.  Leaf items are drained whenever 32 are
-// available, so that stack never holds more than 31 + 64.
+// Queue order and bound.  The order of the items is free, so it serves the batches (see drain): the
+// node queue is a ring, batches take its OLDEST items while it is short (breadth-first: only short
+// subtrees are left at the end of a round) and the newest above that (depth-first: bounded growth).
+// Taken newest-first only, items pushed in reverse lane order keep the queue sorted by tree depth and
+// R + 64*(max_depth+1) entries always suffice; the kernel does not rely on that bound: whenever fewer
+// than 96 entries are free it takes items one at a time (a plain DFS adds at most `depth` < 64 entries
+// before it shrinks), so any ring of >= 256 entries is safe for any content.  Leaf items are drained
+// whenever 32 are available, so that stack never holds more than 31 + 64.
 //
 // Work distribution.  spp == 1 (kSpread = false): a slot owns a pixel (and, for robustness, all its
 // samples), claimed from the global cursor with one warp-aggregated atomicAdd.  spp > 1 (kSpread):
@@ -144,13 +148,10 @@ __global__ void __launch_bounds__(kWqMaxThreads, 1) render_warpqueue_kernel(cons
   // Lane masks.  At 64 registers the compiler does not keep them live across the batch bodies; re-reading %lanemask_lt/gt
   // is one instruction where re-deriving them from the thread index is four, but it also changes the register
   // allocation: measured A/B (profiles/r2_sweep_kernel_ab.json) the special registers win on the packet variants
-  // (irreg 64 spp 13.88 -> 13.49 ms, 1 M spheres 77.6 -> 76.4) and lose on the fully staged one (rgbbox 38.05 -> 38.64).
+  // (irreg 64 spp 13.88 -> 13.49 ms, 1 M spheres 77.6 -> 76.4) and lose on the fully staged one (rgbbox 38.05 -> 38.64;
+  // re-measured after the instruction-cache work: no difference either way, 32.16 vs 32.14 ms).
   unsigned lt_mask, gt_mask;
-#ifdef RAYB200_LANEMASK_ALL
-  if constexpr (true) {
-#else
   if constexpr (kPacket) {
-#endif
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
     asm("mov.u32 %0, %%lanemask_gt;" : "=r"(gt_mask));
   } else {
