@@ -49,6 +49,27 @@ def test_struct_layouts_match_the_library(R):
     assert ctypes.sizeof(R.RenderJob) == lib.ray_b200_render_job_size() == 72
 
 
+def test_tuning_parameters_match_the_documented_environment_variables(R):
+    """futhark_get_tuning_param_* / futhark_context_config_set_tuning_param (host-only calls): every RAY_* variable of
+    INTEGRATION.md's tuning rows exists as a tuning parameter of the same name, unknown names are rejected."""
+    lib = R.load_library()
+    lib.futhark_get_tuning_param_name.restype = ctypes.c_char_p
+    names = {lib.futhark_get_tuning_param_name(i).decode() for i in range(lib.futhark_get_tuning_param_count())}
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    rows = [ln for ln in text.splitlines() if ln.startswith("| `RAY_") and "tuning" in ln]
+    documented = {v.lower() for ln in rows for v in re.findall(r"`RAY_(\w+)`", ln.split("|")[1])}
+    assert {"wq_low", "wq_ncap", "wq_packet", "stage_cap", "lw_slots"} <= documented
+    assert documented <= names, documented - names
+    lib.futhark_context_config_new.restype = ctypes.c_void_p
+    cfg = ctypes.c_void_p(lib.futhark_context_config_new())
+    try:
+        for n in sorted(names):
+            assert lib.futhark_context_config_set_tuning_param(cfg, n.encode(), ctypes.c_size_t(1)) == 0, n
+        assert lib.futhark_context_config_set_tuning_param(cfg, b"no_such_parameter", ctypes.c_size_t(1)) != 0
+    finally:
+        lib.futhark_context_config_free(cfg)
+
+
 def _compile(src, out, extra=()):
     cmd = ["/usr/bin/gcc", "-O3", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", src, "-o", out,
            "-I" + os.path.join(ROOT, "include"), "-L" + os.path.join(ROOT, "raytracers_b200"), "-lray_b200",
