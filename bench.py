@@ -25,7 +25,8 @@ oracle in `parity`.  `--gather nccl` switches N > 1 to tile buffers + one ncclGa
 counts) / its measured duration vs the measured HBM peak - an accounting figure, the scene is shared-memory resident;
 `roofline_issue` = useful thread-instructions of the reference traversal / the chip's issue capacity - the bound that applies;
 `parity` / `extra.*.parity` = differing pixels between the GPU frames and the oracle's row samples of the SAME frames (timed
-workload and the other BASELINE configs); `cpu_baseline` = the CPU oracle (a bit-exact port of the reference's Futhark program;
+workload and the other BASELINE configs), plus - at every N - whether the SHA-256 of the full frames the end-to-end leg
+delivered to host memory equals the oracle's known answers (tests/golden/oracle_frame_hashes.json); `cpu_baseline` = the CPU oracle (a bit-exact port of the reference's Futhark program;
 the Futhark compiler is not available here) on a bounded sample of the same workload.
 
 --impl reference times that same CPU port on all host cores (no GPU work), one bounded sample per step.
@@ -609,6 +610,24 @@ def run_ours(args):
                 rows, pixels, bad = rows_differing(got[name], kept[name], 0, ROW_STEP)
                 parity["scenes"][name]["e2e_host_frame_differing"] = bad
         parity["differing"] = sum(v["differing"] + v.get("e2e_host_frame_differing", 0) for v in parity["scenes"].values())
+
+    if rank == 0 and got is not None and H == 1000 and W == 1000 and SPP == 64:
+        # every pixel of the frames the end-to-end leg delivered to host memory (at N > 1: assembled from all ranks' stores)
+        # against the oracle's known answers for these frames (tests/golden/oracle_frame_hashes.json); never fatal
+        try:
+            import hashlib
+            import numpy as np
+            with open(os.path.join(ROOT, "tests", "golden", "oracle_frame_hashes.json")) as f:
+                known = json.load(f)
+            full = {n: hashlib.sha256(np.ascontiguousarray(got[n], "<i4").tobytes()).hexdigest() == known[f"{n}_{H}x{W}_{SPP}spp"]["sha256_le_i32"]
+                    for n in SCENES}
+            if parity is None:
+                parity = {"vs": "SHA-256 of the oracle's full frames (tests/golden/oracle_frame_hashes.json)", "scenes": {}}
+            for n in SCENES:
+                parity["scenes"].setdefault(n, {})["e2e_host_frame_sha256_equals_oracle_full_frame"] = full[n]
+            parity["differing_frames"] = sum(not v for v in full.values())
+        except Exception as e:  # noqa: BLE001
+            print(f"bench: full-frame known-answer check skipped: {e}", file=sys.stderr)
 
     if rank == 0:
         line = {

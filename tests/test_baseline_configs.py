@@ -81,3 +81,18 @@ def test_large_frame_all_kernels_agree_with_default(R):
     ref = sha(_gpu(R, ("irreg",), 4000, 4000, 1, kernel="mega"))
     for kernel in ("auto", "warpqueue"):
         assert sha(_gpu(R, ("irreg",), 4000, 4000, 1, kernel=kernel)) == ref, kernel
+
+
+@pytest.mark.parametrize("name", ["rgbbox", "irreg"])
+def test_headline_1000x1000_64spp_full_frame_known_answer(R, name):
+    """BASELINE configs[1] / [2], EVERY pixel: SHA-256 of the whole 1000x1000 64-spp frame equals the oracle's
+    (tests/golden/oracle_frame_hashes.json, written by tools/make_oracle_hashes.py: ~45 s of CPU, too slow to render here)."""
+    import hashlib
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_frame_hashes.json")) as f:
+        want = json.load(f)[f"{name}_1000x1000_64spp"]["sha256_le_i32"]
+    for kernel in ("auto", "mega"):
+        got = _gpu(R, (name,), 1000, 1000, 64, kernel=kernel)
+        assert hashlib.sha256(np.ascontiguousarray(got, "<i4").tobytes()).hexdigest() == want, f"{name} 1000^2 64 spp {kernel}"
+
