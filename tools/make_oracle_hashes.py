@@ -1,9 +1,11 @@
 #!/usr/bin/env python
-"""Known answers for the headline frames: SHA-256 of the FULL 1000x1000 frames at 64 samples per pixel (BASELINE.json
-configs[1], [2]) as the CPU oracle renders them (little-endian int32[h][w], the layout futhark_values_i32_2d returns).
+"""Known answers for whole frames: SHA-256 of the FULL frames of the configurations the GPU sweeps time - 1000x1000 at 64
+samples per pixel (BASELINE.json configs[1], [2]), irreg 4000x4000 at 1 spp, rgbbox 2000x2000 at 16 spp and the 1 M-sphere
+scene at 2000x2000, 2 spp - as the CPU oracle renders them (little-endian int32[h][w], the layout futhark_values_i32_2d
+returns).  tools/gpu_dev.py prints the first 64 bits of the same hash for every frame it times.
 
 The oracle reproduces the reference's golden PNGs bit for bit (tests/test_oracle_golden.py); spp > 1 is this repo's extension,
-so these frames are pinned by the oracle only.  About a minute on 8 cores.  Writes tests/golden/oracle_frame_hashes.json,
+so these frames are pinned by the oracle only.  About three minutes on 8 cores.  Writes tests/golden/oracle_frame_hashes.json,
 which the GPU tests and bench.py (N > 1: hashes of the frames the end-to-end leg delivered to host memory) compare against.
 
   python tools/make_oracle_hashes.py
@@ -23,14 +25,15 @@ from oracle import pyoracle as O  # noqa: E402
 
 def main():
     out = {}
-    for name in ("rgbbox", "irreg"):
-        for h, w, spp in ((1000, 1000, 64),):
-            t0 = time.time()
-            pix, _, cnt = O.Scene.named(name).prepare(h, w).render(h, w, spp=spp)
-            out[f"{name}_{h}x{w}_{spp}spp"] = {"sha256_le_i32": hashlib.sha256(np.ascontiguousarray(pix, "<i4").tobytes()).hexdigest(),
-                                               "shape": [h, w], "spp": spp, "segments": int(cnt["segments"]),
-                                               "source": "oracle/oracle.cpp (CPU restatement of ray.fut, bit-exact vs rgbbox.png / irreg.png at 1 spp)"}
-            print(name, out[f"{name}_{h}x{w}_{spp}spp"]["sha256_le_i32"], f"{time.time() - t0:.1f} s", flush=True)
+    for key, name, kw, h, w, spp in (("rgbbox", "rgbbox", {}, 1000, 1000, 64), ("irreg", "irreg", {}, 1000, 1000, 64),
+                                     ("irreg", "irreg", {}, 4000, 4000, 1), ("rgbbox", "rgbbox", {}, 2000, 2000, 16),
+                                     ("random1M", "random", dict(n=1000000, seed=1), 2000, 2000, 2)):
+        t0 = time.time()
+        pix, _, cnt = O.Scene.named(name, **kw).prepare(h, w).render(h, w, spp=spp)
+        out[f"{key}_{h}x{w}_{spp}spp"] = {"sha256_le_i32": hashlib.sha256(np.ascontiguousarray(pix, "<i4").tobytes()).hexdigest(),
+                                          "shape": [h, w], "spp": spp, "segments": int(cnt["segments"]),
+                                          "source": "oracle/oracle.cpp (CPU restatement of ray.fut, bit-exact vs rgbbox.png / irreg.png at 1 spp)"}
+        print(key, h, w, spp, out[f"{key}_{h}x{w}_{spp}spp"]["sha256_le_i32"], f"{time.time() - t0:.1f} s", flush=True)
     with open(os.path.join(ROOT, "tests", "golden", "oracle_frame_hashes.json"), "w") as f:
         json.dump(out, f, indent=1, sort_keys=True)
 
