@@ -167,3 +167,18 @@ def test_per_pixel_cost_sums_to_the_counters_and_shards_evenly(oracle):
         per_rank = [int(D.extract_rank_tiles(it, r, world).sum()) for r in range(world)]
         assert sum(per_rank) == int(it.sum())
         assert max(per_rank) / (sum(per_rank) / world) < 1.05, (world, per_rank)
+
+
+def test_oracle_frame_hashes_file_is_current(oracle):
+    """tests/golden/oracle_frame_hashes.json (full-frame known answers the GPU tests and bench.py compare with; written by
+    tools/make_oracle_hashes.py) still is what the oracle renders - checked on its cheapest entry, irreg 4000x4000 at 1 spp
+    (the north-star frame; 27.7 M segments, a few seconds); the other entries are checked for shape and format."""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_frame_hashes.json")) as f:
+        known = json.load(f)
+    assert set(known) >= {"rgbbox_1000x1000_64spp", "irreg_1000x1000_64spp", "irreg_4000x4000_1spp", "random1M_2000x2000_2spp"}
+    got, _, cnt = oracle.render_scene("irreg", 4000, 4000)
+    want = known["irreg_4000x4000_1spp"]
+    assert sha(got) == want["sha256_le_i32"] and cnt["segments"] == want["segments"] == 27663974
+    assert all(len(v["sha256_le_i32"]) == 64 and v["shape"] == [int(x) for x in k.split("_")[1].split("x")] for k, v in known.items())
