@@ -574,9 +574,21 @@ def run_ours(args):
                 o_sc = O.Scene.named(scene_args[0], **({"n": scene_args[1], "seed": scene_args[2]} if len(scene_args) > 1 else {}))
                 t0 = time.perf_counter()
                 want, _, ocnt = o_sc.prepare(hh, ww).render(hh, ww, spp=spp, row_start=row_start, row_step=row_step, threads=threads)
-                rows, pixels, bad = rows_differing(fr.cpu().numpy(), want, row_start, row_step)
+                fr_host = fr.cpu().numpy()
+                rows, pixels, bad = rows_differing(fr_host, want, row_start, row_step)
                 par = {"rows": rows, "pixels": pixels, "differing": bad, "oracle_segments": ocnt["segments"],
                        "oracle_s": round(time.perf_counter() - t0, 2)}
+                try:   # every pixel: SHA-256 of the whole frame against the oracle's known answer for this config (never fatal)
+                    import hashlib
+                    import numpy as np
+                    with open(os.path.join(ROOT, "tests", "golden", "oracle_frame_hashes.json")) as f:
+                        known = json.load(f).get(tag)
+                    if known:
+                        par["full_frame_sha256_equals_oracle"] = (
+                            hashlib.sha256(np.ascontiguousarray(fr_host, "<i4").tobytes()).hexdigest() == known["sha256_le_i32"])
+                except Exception as e:  # noqa: BLE001
+                    print(f"bench: full-frame known-answer check of {tag} skipped: {e}", file=sys.stderr)
+                del fr_host
             extra[tag] = {"ms_per_frame": round(m, 3), "segments": wk["segments"], "Mrays_s": round(wk["segments"] / m / 1e3, 1),
                           "algorithmic_GB": round(gb, 2), "GB_s": round(gb / m * 1e3, 1), "roofline_frac": round(gb / m * 1e3 / peak, 4),
                           "issue_frac": issue_roofline(wk, m, sm_count, sm_mhz)["frac"], "parity": par,
