@@ -188,6 +188,18 @@ MIN_SPHERE_INSTR = 30
 PUBLISHED_1SPP_MS = {"futhark_multicore_ryzen1700x": {"rgbbox": 179, "irreg": 62}, "futhark_gpu_mi100": {"rgbbox": 14, "irreg": 8}}
 
 
+def full_frame_equals_oracle(frame, key):
+    """True / False: SHA-256 of a whole frame (int32[h][w]) against the oracle's known answer `key` of
+    tests/golden/oracle_frame_hashes.json (tools/make_oracle_hashes.py); None when no answer is recorded for that config."""
+    import hashlib
+    import numpy as np
+    with open(os.path.join(ROOT, "tests", "golden", "oracle_frame_hashes.json")) as f:
+        known = json.load(f).get(key)
+    if not known:
+        return None
+    return hashlib.sha256(np.ascontiguousarray(frame, "<i4").tobytes()).hexdigest() == known["sha256_le_i32"]
+
+
 def issue_roofline(work, ms, sm_count, sm_mhz):
     """Instruction-issue roofline of a render launch: useful thread-instructions of the REFERENCE traversal's box and
     sphere tests / (SMs x 4 schedulers x 32 lanes x clock x time).  This, not HBM, is what bounds the kernel."""
@@ -579,13 +591,9 @@ def run_ours(args):
                 par = {"rows": rows, "pixels": pixels, "differing": bad, "oracle_segments": ocnt["segments"],
                        "oracle_s": round(time.perf_counter() - t0, 2)}
                 try:   # every pixel: SHA-256 of the whole frame against the oracle's known answer for this config (never fatal)
-                    import hashlib
-                    import numpy as np
-                    with open(os.path.join(ROOT, "tests", "golden", "oracle_frame_hashes.json")) as f:
-                        known = json.load(f).get(tag)
-                    if known:
-                        par["full_frame_sha256_equals_oracle"] = (
-                            hashlib.sha256(np.ascontiguousarray(fr_host, "<i4").tobytes()).hexdigest() == known["sha256_le_i32"])
+                    same = full_frame_equals_oracle(fr_host, tag)
+                    if same is not None:
+                        par["full_frame_sha256_equals_oracle"] = same
                 except Exception as e:  # noqa: BLE001
                     print(f"bench: full-frame known-answer check of {tag} skipped: {e}", file=sys.stderr)
                 del fr_host
@@ -627,19 +635,14 @@ def run_ours(args):
         # every pixel of the frames the end-to-end leg delivered to host memory (at N > 1: assembled from all ranks' stores)
         # against the oracle's known answers for these frames (tests/golden/oracle_frame_hashes.json); never fatal
         try:
-            import hashlib
-            import numpy as np
-            with open(os.path.join(ROOT, "tests", "golden", "oracle_frame_hashes.json")) as f:
-                known = json.load(f)
-            full = {n: hashlib.sha256(np.ascontiguousarray(got[n], "<i4").tobytes()).hexdigest() == known[f"{n}_{H}x{W}_{SPP}spp"]["sha256_le_i32"]
-                    for n in SCENES if f"{n}_{H}x{W}_{SPP}spp" in known}
-            if not full:
-                raise KeyError(f"no known answer recorded for {SCENES} at {H}x{W}, {SPP} spp")
-            if parity is None:
-                parity = {"vs": "SHA-256 of the oracle's full frames (tests/golden/oracle_frame_hashes.json)", "scenes": {}}
-            for n in full:
-                parity["scenes"].setdefault(n, {})["e2e_host_frame_sha256_equals_oracle_full_frame"] = full[n]
-            parity["differing_frames"] = sum(not v for v in full.values())
+            full = {n: full_frame_equals_oracle(got[n], f"{n}_{H}x{W}_{SPP}spp") for n in SCENES}
+            full = {n: v for n, v in full.items() if v is not None}
+            if full:
+                if parity is None:
+                    parity = {"vs": "SHA-256 of the oracle's full frames (tests/golden/oracle_frame_hashes.json)", "scenes": {}}
+                for n in full:
+                    parity["scenes"].setdefault(n, {})["e2e_host_frame_sha256_equals_oracle_full_frame"] = full[n]
+                parity["differing_frames"] = sum(not v for v in full.values())
         except Exception as e:  # noqa: BLE001
             print(f"bench: full-frame known-answer check skipped: {e}", file=sys.stderr)
 

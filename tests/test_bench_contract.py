@@ -28,3 +28,17 @@ def test_reference_arm_other_ranks_stay_silent():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
                        capture_output=True, text=True, timeout=60, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_full_frame_known_answer_helper(oracle):
+    """bench.full_frame_equals_oracle (the per-N / per-config `…sha256_equals_oracle…` flags of the JSON line): True for the
+    oracle's own frame, False for a frame with one pixel changed, None for a config without a recorded answer."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    frame, _, _ = oracle.render_scene("irreg", 4000, 4000)
+    assert bench.full_frame_equals_oracle(frame, "irreg_4000x4000_1spp") is True
+    frame[1234, 567] ^= 1
+    assert bench.full_frame_equals_oracle(frame, "irreg_4000x4000_1spp") is False
+    assert bench.full_frame_equals_oracle(frame, "irreg_123x45_6spp") is None
