@@ -340,8 +340,10 @@ int do_render(futhark_context *ctx, RenderParams &P, int lane_id, bool timed, co
     P.tile_order = tb.order;
     L.tile_order_plan = tb;
   }
-  // Learned claim order: frames on the context's stream (lane 0, outside batches: the protocol of main.c, which renders the
-  // same frame `runs` times).  First frame of a geometry: record the longest path per tile; afterwards: long-path tiles first.
+  // Learned claim order (every frame of a prepared scene, single calls - the protocol of main.c, which renders the same
+  // frame `runs` times - and batch frames on either lane alike).  First frame of a geometry: record the longest path per
+  // tile; afterwards: long-path tiles first.  The table belongs to the prepared scene; `ready` orders its sort before
+  // readers on the other lane, the scene's last-use events keep a re-recording away from frames still reading it.
   bool record_order = false;
   // (Frames of more than 2^24 tile-samples do not end on their longest paths any more, and un-mixing cheap and expensive
   // tiles costs them 2 %: irreg 4000^2 at 256 spp 694 -> 708 ms, at 16 spp 59.2 -> 58.4, at 1 spp 3.67 -> 3.28.)
@@ -436,8 +438,6 @@ int do_render(futhark_context *ctx, RenderParams &P, int lane_id, bool timed, co
   ctx->renders++;
   return 0;
 }
-
-// Device memory goes back to the stream-ordered pool (ordered after any render still using it);
 
 }  // namespace rayb200_api
 
